@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py - ViT images/sec (fwd + CE + bwd + AdamW) on the B200 attention hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE for N > 1).  Prints ONE JSON
+line on rank 0.  A "step" is the reference's training step (train.py:108-116: zero_grad -> forward
+-> CrossEntropyLoss -> backward -> AdamW.step) on one synthetic batch.
+
+Keys: ``value`` = whole-job images/s with the batch already resident in HBM; ``e2e`` = the same
+metric through the public module API with pinned-host inputs copied H2D and the loss read back
+every step; ``roofline`` = the fused attention forward kernel, timed per launch with CUDA events
+inside the timed region, against its binding roof; ``cpu_baseline`` = the oracle port of the
+reference (oracle/vit_torch.py, torch CPU fp32) timed on this box's host cores on a bounded
+sample; ``clocks`` = nvidia-smi SM clock / throttle reasons sampled during the timed region.
+``--impl reference`` times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric's "fused-attn % of tensor-core peak" and
+    # the north_star targets are quoted on; fits one GPU.  1000 classes (free choice).
+    "vitb16-224-rope-mixed-bf16": dict(
+        model=dict(img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12,
+                   num_heads=12, pos_encoding="rope-mixed"),
+        batch=256, dtype="bf16", train=True, cpu_sample_batch=8),
+    # configs[0] / configs[1]: ViT-Tiny fp32
+    "vit-tiny-rope-axial-fp32": dict(
+        model=dict(img_size=32, patch_size=4, in_chans=3, num_classes=10, embed_dim=192, depth=6, num_heads=6,
+                   pos_encoding="rope-axial"),
+        batch=128, dtype="f32", train=True, cpu_sample_batch=128),
+    "vit-tiny-polynomial-fp32": dict(
+        model=dict(img_size=32, patch_size=4, in_chans=1, num_classes=10, embed_dim=192, depth=6, num_heads=6,
+                   pos_encoding="polynomial"),
+        batch=128, dtype="f32", train=True, cpu_sample_batch=128),
+    "vit-tiny-relative-fp32": dict(
+        model=dict(img_size=32, patch_size=4, in_chans=3, num_classes=10, embed_dim=192, depth=6, num_heads=6,
+                   pos_encoding="relative"),
+        batch=128, dtype="f32", train=True, cpu_sample_batch=128),
+    # configs[3]: ViT-L/16-384 rope-axial bf16, batch 64/GPU (BASELINE leaves it open)
+    "vitl16-384-rope-axial-bf16": dict(
+        model=dict(img_size=384, patch_size=16, in_chans=3, num_classes=1000, embed_dim=1024, depth=24,
+                   num_heads=16, pos_encoding="rope-axial"),
+        batch=64, dtype="bf16", train=True, cpu_sample_batch=2),
+    # configs[4]: ViT-B/16 built at 224, fed 512x512 (1025 tokens), inference
+    "vitb16-512-rope-mixed-infer-bf16": dict(
+        model=dict(img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12,
+                   num_heads=12, pos_encoding="rope-mixed"),
+        batch=64, dtype="bf16", train=False, input_size=512, cpu_sample_batch=2),
+}
+DEFAULT_WORKLOAD = "vitb16-224-rope-mixed-bf16"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-impl", default="auto", choices=["auto", "simt", "tcgen05"])
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append((float(f[0]), float(f[1]), f[2:6]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        reasons = sorted({n for _, _, fl in self.samples for n, v in zip(self.NAMES, fl) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.samples[0][1],
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def attn_algorithmic(model_cfg, tokens):
+    """Per image, per layer: fwd flops 4*N^2*E; min bytes (bf16) 8*N*E + 4*H*N."""
+    e, h = model_cfg["embed_dim"], model_cfg["num_heads"]
+    return 4.0 * tokens * tokens * e, 8.0 * tokens * e + 4.0 * h * tokens
+
+
+def model_flops_per_image(model_cfg, tokens, train):
+    e, depth, p, c = model_cfg["embed_dim"], model_cfg["depth"], model_cfg["patch_size"], model_cfg["in_chans"]
+    fwd = depth * (24.0 * tokens * e * e + 4.0 * tokens * tokens * e) + 2.0 * (tokens - 1) * c * p * p * e \
+        + 2.0 * e * model_cfg["num_classes"]
+    return fwd * (3.0 if train else 1.0)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+def cpu_reference_run(wl, steps, warmup):
+    """The reference's CPU path (oracle port, torch fp32, all host threads) on a bounded sample."""
+    from oracle import vit_torch as V
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = V.VitConfig(**wl["model"])
+    bs = wl["cpu_sample_batch"]
+    size = wl.get("input_size", cfg.img_size)
+    params = V.params_from_state_dict(V.init_state_dict(cfg, seed=0), requires_grad=wl["train"])
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(bs, cfg.in_chans, size, size, generator=g)
+    labels = torch.randint(0, cfg.num_classes, (bs,), generator=g)
+    opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=1e-3, weight_decay=0.01) \
+        if wl["train"] else None
+
+    def step():
+        if wl["train"]:
+            V.train_step(cfg, params, opt, images, labels)
+        else:
+            with torch.no_grad():
+                V.forward(cfg, params, images)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dict(value=bs * steps / dt, unit="images/s", cores=threads, kind="port",
+                sample=f"{steps} steps of batch {bs} (of the workload's {wl['batch']}/GPU), fp32, "
+                       f"torch {torch.__version__} CPU, {threads} threads"), dt / steps * 1e3
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb, ms = cpu_reference_run(wl, steps, warmup)
+    line = {"impl": "reference", "metric": "ViT images/sec fwd+bwd", "value": cb["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, **wl["model"], "batch_per_step": wl["cpu_sample_batch"],
+                       "train": wl["train"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch.distributed as dist
+    from vit_rpe_rope_b200 import VisionTransformer, _lib, ops
+    from vit_rpe_rope_b200.dp import BucketedDataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    _lib.set_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.attn_impl])
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    mcfg = wl["model"]
+    batch = args.batch or wl["batch"]
+    size = wl.get("input_size", mcfg["img_size"])
+    tokens = (size // mcfg["patch_size"]) ** 2 + 1
+    bf16 = wl["dtype"] == "bf16"
+    torch.manual_seed(0)
+    model = VisionTransformer(**mcfg).to(dev)
+    train = wl["train"]
+    dp = BucketedDataParallel(model, bucket_mb=32.0) if train else None
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True) if train else None
+    if not train:
+        model.eval()
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_images = torch.randn(batch, mcfg["in_chans"], size, size, generator=g).pin_memory()
+    host_labels = torch.randint(0, mcfg["num_classes"], (batch,), generator=g).pin_memory()
+    dev_images, dev_labels = host_images.to(dev), host_labels.to(dev)
+
+    def step(images, labels):
+        if train:
+            dp.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+                logits = dp(images)
+                loss = F.cross_entropy(logits.float(), labels)
+            loss.backward()
+            dp.sync()
+            opt.step()
+            return loss
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            return dp(images) if dp else model(images)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for _ in range(args.warmup):
+        step(dev_images, dev_labels)
+
+    # ---- timed region 1: device-resident inputs -> `value`, per-launch attention timing -> `roofline`
+    sampler = ClockSampler(local_rank)
+    ops.PROFILE_EVENTS = []
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dev_images, dev_labels)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = _lib.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
+    kernel_ms = {}
+    for name, a, b in events:
+        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
+
+    # ---- timed region 2: end to end through the public API with pinned-host inputs -> `e2e`
+    for _ in range(2):
+        step(host_images.to(dev, non_blocking=True), host_labels.to(dev, non_blocking=True))
+    barrier()
+    e0.record()
+    last = None
+    for _ in range(args.steps):
+        imgs = host_images.to(dev, non_blocking=True)
+        lbls = host_labels.to(dev, non_blocking=True)
+        out = step(imgs, lbls)
+        last = out.item() if train else float(out.float().cpu()[0, 0])  # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    h2d = host_images.numel() * host_images.element_size() + host_labels.numel() * host_labels.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = world * batch * args.steps / (ms_total / 1e3)
+    e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
+    flops_img, bytes_img = attn_algorithmic(mcfg, tokens)
+    roofline, extra = None, {}
+    if "attn_fwd" in kernel_ms:
+        avg_ms = statistics.mean(kernel_ms["attn_fwd"])
+        flops, byts = flops_img * batch, bytes_img * batch * (1.0 if bf16 else 2.0)
+        tf, gbs = flops / avg_ms / 1e9, byts / avg_ms / 1e6
+        intensity = flops / byts
+        ridge = peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"]
+        if intensity < ridge or not bf16:
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+        else:
+            roofline = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None}
+        roofline.update({"kernel": "vrr_attn_fwd", "avg_launch_ms": avg_ms, "launches_timed": len(kernel_ms["attn_fwd"]),
+                         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts,
+                         "tflops": tf, "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
+                         "peak_source": peaks["source"] + (" (sustained: kernel timed inside a long step)")})
+    for name, arr in kernel_ms.items():
+        extra[name] = {"avg_launch_ms": statistics.mean(arr), "launches": len(arr)}
+        if name == "attn_bwd":
+            extra[name]["tflops"] = 2 * flops_img * batch / statistics.mean(arr) / 1e9
+    step_tflops = model_flops_per_image(mcfg, tokens, train) * value / 1e12
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(wl, steps=3, warmup=1)
+
+    line = {
+        "metric": "ViT images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": wl["dtype"], "data": "synthetic",
+        "config": {"workload": args.workload, **mcfg, "tokens": tokens, "batch_per_gpu": batch,
+                   "global_batch": batch * world, "train": train, "optimizer": "AdamW(lr=1e-3, wd=0.01)" if train else None,
+                   "parallelism": f"dp{world}", "l2": "inputs+activations per step exceed the 126 MB L2 (no flush needed)",
+                   "attn_impl": args.attn_impl},
+        "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else int(out.numel() * 4)},
+        "gpu_launches": int(gpu_launches),
+        "roofline": roofline, "hot_path_kernels": extra, "model_tflops": step_tflops,
+        "mfu_vs_bf16_sustained": step_tflops / peaks["bf16_tflops_sustained"] if bf16 else None,
+        "cpu_baseline": cpu_baseline, "clocks": clocks, "last_result": last,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

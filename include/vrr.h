@@ -1,0 +1,155 @@
+/*
+ * vrr.h - C ABI of libvrr_b200.so: the B200 (sm_100a) ViT attention hot path of
+ * zhengyk19/vit-rpe-rope.
+ *
+ * The reference is pure Python/PyTorch and has NO FFI / plugin boundary of its own
+ * (SURVEY.md section 8, row B1): its boundary is the Python module API of models/.  This header
+ * is therefore the boundary a maintainer would bind from that API (INTEGRATION.md shows the
+ * ctypes stub).  Each entry point names the reference code (file:line under /root/reference) it
+ * replaces.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only: no torch / pybind / C++ types cross this boundary;
+ *   - every data pointer is a DEVICE pointer on the current CUDA device (sm_100); the library
+ *     never allocates, never synchronises, never throws; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value: VRR_OK (0) or a negative vrr_status; vrr_last_error() gives the reason;
+ *   - tensors are dense row-major with the shapes documented per argument; `dtype` selects the
+ *     element type of activations/weights (VRR_F32 or VRR_BF16).  Position tables (cos/sin, bias
+ *     table, polynomial coefficients), softmax statistics and all parameter-gradient outputs that
+ *     are reductions (d_table, d_coef, d_cos, d_sin) are ALWAYS fp32;
+ *   - there is no CPU path: on a machine without an sm_100 device every compute entry point
+ *     returns VRR_ERR_NO_DEVICE.
+ *
+ * Token / head geometry: B images, N tokens per image (token 0 is the cls token, tokens 1..N-1 are
+ * the g*g patches in raster order), E = H * Dh channels, H heads of Dh channels.  Dh must be one of
+ * 16, 32, 64 (the tcgen05 bf16 kernels need Dh == 64).
+ *
+ * "qkv planes": one buffer [3][B][H][N][Dh] holding q (rotated when RoPE is on), k (likewise), v.
+ */
+#ifndef VRR_H_
+#define VRR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRR_ABI_VERSION 1
+
+typedef enum {
+  VRR_OK = 0,
+  VRR_ERR_INVALID_ARG = -1,   /* null pointer, bad enum, inconsistent sizes            */
+  VRR_ERR_UNSUPPORTED = -2,   /* shape/dtype outside what the kernels implement         */
+  VRR_ERR_NO_DEVICE = -3,     /* no CUDA device, or the current device is not sm_100    */
+  VRR_ERR_CUDA = -4,          /* a CUDA runtime/driver call failed (see vrr_last_error) */
+  VRR_ERR_WORKSPACE = -5      /* workspace too small (see vrr_*_workspace_bytes)        */
+} vrr_status;
+
+typedef enum { VRR_F32 = 0, VRR_BF16 = 1 } vrr_dtype;
+
+/* RoPE variants of models/vit.py:51-68.  AXIAL: cos/sin are [N-1][Dh/2] shared by all heads
+ * (positional_encoding.py:216-245).  MIXED: cos/sin are [H][N-1][Dh/2]
+ * (positional_encoding.py:313-351).  Token 0 (cls) is never rotated (vit.py:56-57). */
+typedef enum { VRR_ROPE_NONE = 0, VRR_ROPE_AXIAL = 1, VRR_ROPE_MIXED = 2 } vrr_rope_mode;
+
+/* Additive logit bias of models/vit.py:73-81.
+ * TABLE: relative-position table [H][2N-1]; bias[h][i][j] = table[h][i - j + N - 1]
+ *        (positional_encoding.py:58-75,93).
+ * POLY : polynomial in the L1 patch distance, coef [Hc][degree+1] with Hc = 1 (shared) or H;
+ *        bias[h][i][j] = sum_k coef[k] * d^k for i,j >= 1, 0 on the cls row/column, with
+ *        d = |(i-1)%g - (j-1)%g| + |(i-1)/g - (j-1)/g| (positional_encoding.py:127-171). */
+typedef enum { VRR_BIAS_NONE = 0, VRR_BIAS_TABLE = 1, VRR_BIAS_POLY = 2 } vrr_bias_mode;
+
+/* Kernel family selection for the bf16 attention / QKV kernels.  AUTO picks the tcgen05 (tensor
+ * core, TMEM) kernels whenever the shape allows and the SIMT kernels otherwise; the other two
+ * force one family (tests use them to cross-check).  fp32 always runs the SIMT FFMA kernels:
+ * tcgen05 has no fp32 MMA and the fp32 parity bar is 1e-5. */
+typedef enum { VRR_IMPL_AUTO = 0, VRR_IMPL_SIMT = 1, VRR_IMPL_TCGEN05 = 2 } vrr_impl;
+
+typedef struct {
+  int32_t mode;        /* vrr_bias_mode                                                  */
+  int32_t heads;       /* rows of `param`: H for TABLE; 1 or H for POLY                  */
+  int32_t len;         /* columns of `param`: 2N-1 for TABLE; degree+1 for POLY          */
+  int32_t grid;        /* POLY: patch grid side g (N-1 == g*g); ignored otherwise        */
+  const float* param;  /* fp32 [heads][len]; NULL when mode == NONE                      */
+} vrr_bias_desc;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int vrr_abi_version(void);
+const char* vrr_last_error(void);          /* thread-local, valid until the next call           */
+int vrr_device_ok(void);                   /* 1 if the current device is sm_100, else 0         */
+int vrr_set_impl(int impl);                /* vrr_impl; process-wide; returns previous value    */
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+uint64_t vrr_launch_count(void);
+
+/* ---- (c) patch embedding: models/vit.py:164,248-258 ---------------------------------------- */
+/* tokens[b][0][:]   = cls_token
+ * tokens[b][1+p][:] = round_dtype(conv_weight[E][C*P*P] . unfold(images)[b][p][:] + conv_bias) (+ pos_embed[p])
+ * images [B][C][Hi][Wi], weight [E][C][P][P], bias [E]            : element type `dtype`
+ * cls_token [E], pos_embed, tokens [B][Np+1][E]                    : element type `tok_dtype`
+ * pos_embed: NULL, or the absolute table [>= Np][E] (positional_encoding.py:37-40: added to patch
+ * rows only).  (dtype, tok_dtype) = (bf16, fp32) is the reference's autocast semantics: the conv
+ * result is bf16, the concatenation with the fp32 cls token promotes the stream to fp32. */
+int vrr_patch_embed_fwd(const void* images, const void* weight, const void* bias,
+                        const void* cls_token, const void* pos_embed, void* tokens,
+                        int B, int C, int Hi, int Wi, int P, int E, int dtype, int tok_dtype,
+                        void* stream);
+/* d_tokens [B][Np+1][E] (`tok_dtype`).  Parameter gradients are reductions and ALWAYS fp32:
+ * d_weight [E][C*P*P], d_bias [E], d_cls [E], d_pos [Np][E] or NULL; written (not accumulated).
+ * Images need no gradient (train.py:109-115). */
+int vrr_patch_embed_bwd(const void* images, const void* d_tokens, void* d_weight, void* d_bias,
+                        void* d_cls, void* d_pos, int B, int C, int Hi, int Wi, int P, int E,
+                        int dtype, int tok_dtype, void* stream);
+
+/* ---- (a) QKV projection with RoPE epilogue: models/vit.py:47-68, rope_utils.py:3-37 -------- */
+/* planes = split_heads(x . w_qkv^T) with q,k rows 1.. rotated by (cos,sin) in the epilogue.
+ * x [B*N][E], w_qkv [3E][E] (row order (3,H,Dh), vit.py:47), cos/sin fp32 (see vrr_rope_mode),
+ * planes [3][B][H][N][Dh]. */
+int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, const float* sin_tab,
+                     void* planes, int B, int N, int E, int H, int rope_mode, int dtype,
+                     void* stream);
+/* Backward of the epilogue: un-rotates d_planes into token layout and reduces the table grads.
+ * d_planes [3][B][H][N][Dh] (grads w.r.t. rotated q,k and v), planes = forward output,
+ * d_qkv [B*N][3E] (gradient of x . w_qkv^T, ready for the two plain GEMMs dX = d_qkv . W and
+ * dW = d_qkv^T . x), d_cos/d_sin fp32 with the shape of cos/sin or NULL (skipped), written. */
+int vrr_qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab,
+                     const float* sin_tab, void* d_qkv, float* d_cos, float* d_sin, int B, int N,
+                     int E, int H, int rope_mode, int dtype, void* stream);
+
+/* Stand-alone rotate-half of rope_utils.py:3-37 (the public apply_rotary_emb): q,k [B][H][Nr][Dh]
+ * dense, cos/sin fp32 [Nr][Dh/2] (AXIAL) or [H][Nr][Dh/2] (MIXED); every row is rotated.
+ * inverse != 0 applies the transpose rotation (the gradient w.r.t. q,k). */
+int vrr_rope_apply(const void* q_in, const void* k_in, const float* cos_tab, const float* sin_tab,
+                   void* q_out, void* k_out, int B, int H, int Nr, int Dh, int rope_mode,
+                   int inverse, int dtype, void* stream);
+
+/* Plain GEMM used by the backward of the projection: C = op(A) . op(B), row-major operands,
+ * op(A) is [M][K] (trans_a: A is stored [K][M]), op(B) is [K][N] (trans_b: B is stored [N][K]).
+ * `dtype` is the element type of A and B, `c_dtype` that of C (fp32 C is allowed for bf16 inputs:
+ * weight gradients).  fp32 accumulation always. */
+int vrr_gemm(const void* a, const void* b, void* c, int M, int N, int K, int trans_a, int trans_b,
+             int dtype, int c_dtype, void* stream);
+
+/* ---- (b) fused attention: models/vit.py:71-88 ---------------------------------------------- */
+/* out = merge_heads(softmax(q k^T * scale + bias) v), lse = log-sum-exp of the logits.
+ * planes [3][B][H][N][Dh], out [B][N][H*Dh], lse fp32 [B][H][N].  scale = Dh^-0.5 (vit.py:32),
+ * applied after q k^T and before the bias (vit.py:71,75). */
+int vrr_attn_fwd(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B,
+                 int H, int N, int Dh, float scale, int dtype, void* stream);
+size_t vrr_attn_bwd_workspace_bytes(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
+/* d_planes [3][B][H][N][Dh] (dq, dk, dv w.r.t. the planes), written.
+ * d_bias_param fp32 [bias->heads][bias->len] or NULL: gradient of the table / coefficients summed
+ * over the batch, written (not accumulated).  workspace: device scratch of at least
+ * vrr_attn_bwd_workspace_bytes() bytes. */
+int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out,
+                 const float* lse, void* d_planes, float* d_bias_param, void* workspace,
+                 size_t workspace_bytes, int B, int H, int N, int Dh, float scale, int dtype,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRR_H_ */

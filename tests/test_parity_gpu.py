@@ -1,0 +1,426 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): index / coordinate tables bit-exact (CPU tests); logits and
+gradients max-abs <= 1e-5 in fp32 and <= 2e-2 relative in bf16.  "max-abs" is scaled by
+max(1, max|reference|) per tensor so that large-magnitude gradients are held to 1e-5 *relative to
+their scale*; "relative" for bf16 is max|a-b| / max|b|.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import attention_np as A
+from oracle import tables_np as T
+from oracle import vit_torch as V
+from vit_rpe_rope_b200 import _lib, models, ops
+from vit_rpe_rope_b200.models.vit import Attention, VisionTransformer
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+MODES = ("none", "absolute", "relative", "polynomial", "rope-axial", "rope-mixed")
+MODEL_TAGS = ["none", "absolute", "relative", "polynomial", "polynomial_perhead", "rope_axial", "rope_mixed"]
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def err_scaled(got, want):
+    got = torch.as_tensor(got).detach().double().cpu()
+    want = torch.as_tensor(want).detach().double().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return (got - want).abs().max().item() / max(1.0, want.abs().max().item())
+
+
+def err_rel(got, want):
+    got = torch.as_tensor(got).detach().double().cpu()
+    want = torch.as_tensor(want).detach().double().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return (got - want).abs().max().item() / max(want.abs().max().item(), 1e-30)
+
+
+# ------------------------------------------------------------------------------------- golden: model
+
+@pytest.mark.parametrize("tag", MODEL_TAGS)
+def test_model_vs_reference_golden_fp32(tag):
+    """Small ViT: logits, loss and every parameter gradient against outputs of the reference itself."""
+    z = np.load(os.path.join(GOLDEN, f"model_{tag}.npz"))
+    kw = eval(str(z["kwargs"]))  # noqa: S307
+    model = VisionTransformer(**kw)
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    model = model.to(DEV)
+    before = _lib.launch_count()
+    logits = model(torch.from_numpy(z["images"]).to(DEV))
+    loss = F.cross_entropy(logits, torch.from_numpy(z["labels"]).to(DEV))
+    loss.backward()
+    assert _lib.launch_count() > before, "no libvrr kernel was launched"
+    assert err_scaled(logits, z["logits"]) <= FP32_TOL
+    assert abs(loss.item() - float(z["loss"])) <= FP32_TOL
+    checked = 0
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        assert err_scaled(p.grad, z["grad." + name]) <= FP32_TOL, name
+        checked += 1
+    assert checked == sum(1 for k in z.files if k.startswith("grad.") and ".attn.pos_encoding." not in k)
+
+
+# ------------------------------------------------------------------------------------- golden: attention
+
+@pytest.mark.parametrize("tag", [t for t in MODEL_TAGS if t != "absolute"])
+def test_attention_module_vs_reference_golden_fp32(tag):
+    z = np.load(os.path.join(GOLDEN, f"attn_{tag}.npz"))
+    heads, n = 3, 65
+    e = z["x"].shape[-1]
+    attn = Attention(e, num_heads=heads)
+    mode = {"none": "none", "relative": "relative", "polynomial": "polynomial", "polynomial_perhead": "polynomial",
+            "rope_axial": "rope-axial", "rope_mixed": "rope-mixed"}[tag]
+    pe = {"none": models.NoPositionalEncoding(),
+          "relative": models.RelativePositionalEncoding(n - 1, heads),
+          "polynomial": models.PolynomialRPE(n - 1, 3, heads, tag == "polynomial"),
+          "rope-axial": models.RoPEAxial(e // heads, 100.0),
+          "rope-mixed": models.RoPEMixed(e // heads, heads, 100.0)}[mode]
+    attn.set_pos_encoding(pe)
+    attn.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    attn = attn.to(DEV)
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    freqs = pe.get_freqs_cis(n - 1, DEV) if mode.startswith("rope") else None
+    if freqs is not None:
+        assert err_scaled(freqs[0], z["cos"]) <= 2e-6 and err_scaled(freqs[1], z["sin"]) <= 2e-6
+    y = attn(x, freqs_cis=freqs)
+    (y * torch.from_numpy(z["dy"]).to(DEV)).sum().backward()
+    assert err_scaled(y, z["y"]) <= FP32_TOL
+    assert err_scaled(x.grad, z["dx"]) <= FP32_TOL
+    for name, p in attn.named_parameters():
+        assert err_scaled(p.grad, z["grad." + name]) <= FP32_TOL, name
+
+
+# ------------------------------------------------------------------------------------- oracle: ViT-Tiny
+
+def _tiny_kwargs(mode, **over):
+    kw = dict(img_size=32, patch_size=4, in_chans=3, num_classes=10, embed_dim=192, depth=6, num_heads=6,
+              pos_encoding=mode)
+    kw.update(over)
+    return kw
+
+
+def _build_pair(kw, seed=0):
+    torch.manual_seed(seed)
+    model = VisionTransformer(**kw)
+    with torch.no_grad():  # make zero-initialised paths live
+        model.cls_token.normal_(std=0.02)
+        for n, p in model.named_parameters():
+            if n.endswith(".bias"):
+                p.normal_(std=0.02)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    return model.to(DEV), sd
+
+
+def _oracle_run(kw, sd, images, labels, device="cpu", autocast=False):
+    cfg = V.VitConfig(**kw)
+    p = V.params_from_state_dict(sd, device=device)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        logits = V.forward(cfg, p, images.to(device))
+        loss = F.cross_entropy(logits.float(), labels.to(device))
+    loss.backward()
+    return logits.detach(), {k: v.grad for k, v in p.items() if v.is_floating_point() and v.grad is not None}
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("chans", [3, 1])
+def test_vit_tiny_fp32_vs_oracle(mode, chans):
+    """BASELINE configs[0]/[1]: ViT-Tiny (65 tokens, Dh 32), CIFAR- and MNIST-shaped, every mode."""
+    kw = _tiny_kwargs(mode, in_chans=chans)
+    model, sd = _build_pair(kw)
+    torch.manual_seed(1)
+    images, labels = torch.randn(8, chans, 32, 32), torch.randint(0, 10, (8,))
+    logits = model(images.to(DEV))
+    F.cross_entropy(logits, labels.to(DEV)).backward()
+    want, grads = _oracle_run(kw, sd, images, labels)
+    assert err_scaled(logits, want) <= FP32_TOL
+    for name, p in model.named_parameters():
+        assert err_scaled(p.grad, grads[name]) <= FP32_TOL, name
+
+
+def test_vit_tiny_polynomial_per_head_fp32():
+    kw = _tiny_kwargs("polynomial", poly_shared_heads=False, depth=2)
+    model, sd = _build_pair(kw)
+    with torch.no_grad():
+        model.pos_embed.coefficients.mul_(0.3)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    images, labels = torch.randn(4, 3, 32, 32), torch.randint(0, 10, (4,))
+    logits = model(images.to(DEV))
+    F.cross_entropy(logits, labels.to(DEV)).backward()
+    want, grads = _oracle_run(kw, sd, images, labels)
+    assert err_scaled(logits, want) <= FP32_TOL
+    for name, p in model.named_parameters():
+        assert err_scaled(p.grad, grads[name]) <= FP32_TOL, name
+
+
+@pytest.mark.parametrize("mode", ["none", "absolute", "rope-axial", "rope-mixed"])
+def test_resolution_extrapolation_fp32(mode):
+    """vit.py:249,265: the token count follows the INPUT; rope / none / absolute accept larger images."""
+    kw = _tiny_kwargs(mode, depth=2)
+    model, sd = _build_pair(kw)
+    images, labels = torch.randn(2, 3, 64, 64), torch.randint(0, 10, (2,))
+    logits = model(images.to(DEV))
+    F.cross_entropy(logits, labels.to(DEV)).backward()
+    want, grads = _oracle_run(kw, sd, images, labels)
+    assert err_scaled(logits, want) <= FP32_TOL
+    for name, p in model.named_parameters():
+        assert err_scaled(p.grad, grads[name]) <= FP32_TOL, name
+
+
+@pytest.mark.parametrize("mode", ["relative", "polynomial"])
+def test_fixed_size_bias_rejects_other_resolutions(mode):
+    """Reference behaviour (SURVEY aux table): relative / polynomial fail when N != construction N."""
+    model, _ = _build_pair(_tiny_kwargs(mode, depth=1))
+    with pytest.raises(RuntimeError):
+        model(torch.randn(1, 3, 64, 64, device=DEV))
+
+
+# ------------------------------------------------------------------------------------- bf16 (autocast)
+
+@pytest.mark.parametrize("mode", MODES)
+def test_vit_bf16_autocast_vs_reference_semantics(mode):
+    """bf16 = the reference ops under torch.autocast('cuda', bfloat16) with fp32 master weights
+    (SURVEY row O4).  Head dim 64 (ViT-B geometry, shortened) so the tcgen05 kernels are the ones
+    exercised when the library selects them.  Error is measured against the fp32 oracle and must be
+    within 2e-2 relative of it, and not worse than 3x the reference-autocast path's own error."""
+    kw = dict(img_size=64, patch_size=8, in_chans=3, num_classes=10, embed_dim=256, depth=2, num_heads=4,
+              pos_encoding=mode)
+    model, sd = _build_pair(kw)
+    torch.manual_seed(2)
+    images, labels = torch.randn(16, 3, 64, 64), torch.randint(0, 10, (16,))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = model(images.to(DEV))
+        loss = F.cross_entropy(logits.float(), labels.to(DEV))
+    loss.backward()
+    want32, grads32 = _oracle_run(kw, sd, images, labels, device=DEV)
+    want16, grads16 = _oracle_run(kw, sd, images, labels, device=DEV, autocast=True)
+    e_mine, e_ref = err_rel(logits.float(), want32), err_rel(want16.float(), want32)
+    assert e_mine <= BF16_TOL and e_mine <= 3 * e_ref + 2e-3, (e_mine, e_ref)
+    for name, p in model.named_parameters():
+        e_mine, e_ref = err_rel(p.grad, grads32[name]), err_rel(grads16[name], grads32[name])
+        assert p.grad.dtype == torch.float32
+        assert e_mine <= max(BF16_TOL, 3 * e_ref), (name, e_mine, e_ref)
+
+
+# ------------------------------------------------------------------------------------- kernels vs numpy
+
+def _planes(b, h, n, d, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(3, b, h, n, d, generator=g) * 0.8).to(dtype)
+
+
+def _bias_case(kind, h, n, seed=0):
+    g = torch.Generator().manual_seed(seed + 5)
+    if kind == "none":
+        return _lib.BIAS_NONE, None, 0, None
+    if kind == "table":
+        tab = torch.randn(h, 2 * n - 1, generator=g) * 0.5
+        return _lib.BIAS_TABLE, tab, 0, T.relative_bias(tab.numpy().astype(np.float64), n)
+    shared = kind == "poly"
+    grid = int(round((n - 1) ** 0.5))
+    coef = torch.randn(4, generator=g) * 0.02 if shared else torch.randn(h, 4, generator=g) * 0.02
+    return _lib.BIAS_POLY, coef, grid, T.poly_bias(coef.numpy(), n - 1, h).astype(np.float64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,d", [(1, 16), (2, 32), (17, 16), (65, 32), (65, 64), (197, 64), (200, 64), (257, 64)])
+@pytest.mark.parametrize("kind", ["none", "table", "poly", "poly_perhead"])
+def test_attention_kernels_vs_numpy(dtype, n, d, kind):
+    """Fused attention fwd + bwd (whatever kernel family the library selects) vs float64 numpy,
+    ragged and edge sizes: N = 1, N not a multiple of any tile, N > one tile."""
+    if kind.startswith("poly") and int(round((n - 1) ** 0.5)) ** 2 != n - 1:
+        pytest.skip("polynomial bias needs a square patch grid")
+    if kind.startswith("poly") and n == 1:
+        pytest.skip("no patches")
+    b, h = 2, 3
+    mode, param, grid, bias_np = _bias_case(kind, h, n)
+    planes = _planes(b, h, n, d, dtype).to(DEV).requires_grad_(True)
+    prm = None if param is None else param.to(DEV).requires_grad_(True)
+    scale = d ** -0.5
+    out = ops.fused_attention(planes, scale, mode, prm, grid)
+    g = torch.Generator().manual_seed(9)
+    d_out = torch.randn(b, n, h * d, generator=g).to(dtype)
+    out.backward(d_out.to(DEV))
+    pl = planes.detach().double().cpu().numpy()
+    o_np, _, _, _ = A.attention_forward(pl[0], pl[1], pl[2], scale, bias_np)
+    gr = A.attention_backward(d_out.double().numpy(), pl[0], pl[1], pl[2], scale, bias_np)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    e = err_scaled if dtype == torch.float32 else err_rel
+    assert e(out.float(), o_np) <= tol
+    want = np.stack([gr["dq"], gr["dk"], gr["dv"]])
+    assert e(planes.grad.float(), want) <= tol
+    if kind == "table":
+        assert e(prm.grad, A.dtable_from_dbias(gr["dbias"])) <= tol
+    if kind.startswith("poly"):
+        assert e(prm.grad, A.dcoef_from_dbias(gr["dbias"], 3, shared=(kind == "poly"))) <= 5 * tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rope", ["none", "axial", "mixed"])
+@pytest.mark.parametrize("b,n,e,h", [(2, 17, 32, 2), (3, 65, 192, 6), (2, 197, 256, 4), (1, 5, 64, 1)])
+def test_qkv_rope_kernel_vs_numpy(dtype, rope, b, n, e, h):
+    """QKV projection + RoPE epilogue fwd/bwd vs float64 numpy (rotate-half pairs (d, d+Dh/2), cls row
+    un-rotated), including d_cos / d_sin."""
+    if rope != "none" and int(round((n - 1) ** 0.5)) ** 2 != n - 1:
+        pytest.skip("square grid only")
+    dh = e // h
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(b, n, e, generator=g).to(dtype)
+    w = (torch.randn(3 * e, e, generator=g) * e ** -0.5).to(dtype)
+    cos = sin = None
+    if rope != "none":
+        shape = (n - 1, dh // 2) if rope == "axial" else (h, n - 1, dh // 2)
+        ang = torch.rand(*shape, generator=g) * 6.0
+        cos, sin = torch.cos(ang), torch.sin(ang)
+    xs, ws = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    cs = None if cos is None else cos.to(DEV).requires_grad_(True)
+    sn = None if sin is None else sin.to(DEV).requires_grad_(True)
+    planes = ops.QkvRopeFn.apply(xs, ws, cs, sn, h)
+    d_pl = torch.randn(3, b, h, n, dh, generator=g).to(dtype)
+    planes.backward(d_pl.to(DEV))
+    # float64 restatement
+    xd, wd = x.double().numpy(), w.double().numpy()
+    qkv = (xd @ wd.T).reshape(b, n, 3, h, dh).transpose(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    if cos is not None:
+        qr, kr = A.apply_rope_skip_cls(q, k, cos.numpy(), sin.numpy())
+    else:
+        qr, kr = q, k
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    e_ = err_scaled if dtype == torch.float32 else err_rel
+    assert e_(planes.float(), np.stack([qr, kr, v])) <= tol
+    gpl = d_pl.double().numpy()
+    dq, dk, dv = gpl[0].copy(), gpl[1].copy(), gpl[2]
+    if cos is not None:
+        c, s = A._bcast_cs(cos.double().numpy()), A._bcast_cs(sin.double().numpy())
+        d2 = dh // 2
+        dc = np.zeros((b, h, n - 1, d2))
+        ds_ = np.zeros((b, h, n - 1, d2))
+        for x0, g0 in ((q, gpl[0]), (k, gpl[1])):
+            x1, x2 = x0[:, :, 1:, :d2], x0[:, :, 1:, d2:]
+            g1, g2 = g0[:, :, 1:, :d2], g0[:, :, 1:, d2:]
+            dc += g1 * x1 + g2 * x2
+            ds_ += -g1 * x2 + g2 * x1
+        dq[:, :, 1:] = A.rotate_half_inverse(gpl[0][:, :, 1:], c, s)
+        dk[:, :, 1:] = A.rotate_half_inverse(gpl[1][:, :, 1:], c, s)
+        red = (0,) if rope == "mixed" else (0, 1)
+        assert e_(cs.grad, dc.sum(red)) <= 5 * tol
+        assert e_(sn.grad, ds_.sum(red)) <= 5 * tol
+    dqkv = np.stack([dq, dk, dv]).transpose(1, 3, 0, 2, 4).reshape(b * n, 3 * e)
+    assert e_(xs.grad.float(), (dqkv @ wd).reshape(b, n, e)) <= tol
+    assert e_(ws.grad.float(), dqkv.T @ xd.reshape(b * n, e)) <= (tol if dtype == torch.float32 else 2 * tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("b,c,hw,p,e,absolute", [(2, 3, 16, 4, 32, False), (3, 1, 32, 4, 192, True),
+                                                  (2, 3, 64, 16, 128, True), (1, 3, 24, 8, 80, False)])
+def test_patch_embed_kernel_vs_conv2d(dtype, b, c, hw, p, e, absolute):
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(b, c, hw, hw, generator=g).to(dtype)
+    w = (torch.randn(e, c, p, p, generator=g) * 0.1).to(dtype)
+    bias = (torch.randn(e, generator=g) * 0.1).to(dtype)
+    cls = (torch.randn(1, 1, e, generator=g) * 0.1).to(dtype)
+    pos = (torch.randn(1, 100, e, generator=g) * 0.1).to(dtype) if absolute else None
+    leaves = [t.to(DEV).requires_grad_(True) if t is not None else None for t in (w, bias, cls, pos)]
+    tok = ops.PatchEmbedFn.apply(img.to(DEV), *leaves, p)
+    d_tok = torch.randn(tok.shape, generator=g).to(dtype)
+    tok.backward(d_tok.to(DEV))
+    ref_leaves = [t.double().requires_grad_(True) if t is not None else None for t in (w, bias, cls, pos)]
+    y = F.conv2d(img.double(), ref_leaves[0], ref_leaves[1], stride=p).flatten(2).transpose(1, 2)
+    y = torch.cat([ref_leaves[2].expand(b, -1, -1), y], dim=1)
+    if absolute:
+        y = torch.cat([y[:, :1], y[:, 1:] + ref_leaves[3][:, : y.shape[1] - 1]], dim=1)
+    y.backward(d_tok.double())
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    e_ = err_scaled if dtype == torch.float32 else err_rel
+    assert e_(tok.float(), y) <= tol
+    for got, want in zip(leaves, ref_leaves):
+        if got is not None:
+            assert e_(got.grad.float(), want.grad) <= tol
+
+
+@pytest.mark.parametrize("rope", ["axial", "mixed"])
+def test_apply_rotary_emb_public_function(rope):
+    b, h, n, d = 2, 3, 16, 32
+    g = torch.Generator().manual_seed(6)
+    q, k = torch.randn(b, h, n, d, generator=g), torch.randn(b, h, n, d, generator=g)
+    ang = torch.rand(*((n, d // 2) if rope == "axial" else (h, n, d // 2)), generator=g) * 6
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    qd, kd = q.to(DEV).requires_grad_(True), k.to(DEV).requires_grad_(True)
+    tgt = qd
+    qo, ko = models.apply_rotary_emb(qd, kd, models.reshape_for_broadcast(cos.to(DEV), tgt),
+                                     models.reshape_for_broadcast(sin.to(DEV), tgt))
+    c, s = A._bcast_cs(cos.double().numpy()), A._bcast_cs(sin.double().numpy())
+    assert err_scaled(qo, A.rotate_half(q.double().numpy(), c, s)) <= FP32_TOL
+    assert err_scaled(ko, A.rotate_half(k.double().numpy(), c, s)) <= FP32_TOL
+    (qo.sum() + 2 * ko.sum()).backward()
+    ones = np.ones((b, h, n, d))
+    assert err_scaled(qd.grad, A.rotate_half_inverse(ones, c, s)) <= FP32_TOL
+    assert err_scaled(kd.grad, 2 * A.rotate_half_inverse(ones, c, s)) <= FP32_TOL
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(64, 64, 64), (130, 70, 33), (576, 192, 520), (5, 3, 1000)])
+def test_plain_gemm_fp32(ta, tb, m, n, k):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn((k, m) if ta else (m, k), generator=g).to(DEV)
+    b = torch.randn((n, k) if tb else (k, n), generator=g).to(DEV)
+    c = torch.empty(m, n, device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.vrr_gemm(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(c.data_ptr()),
+                      m, n, k, ta, tb, 0, 0, st)
+    assert rc == 0, _lib.last_error()
+    want = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    assert err_scaled(c, want) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------- full-size properties
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind", ["none", "table", "poly"])
+def test_attention_properties_at_vitb_size(dtype, kind):
+    """BASELINE full size (ViT-B/16-224 geometry: 197 tokens, 12 heads, Dh 64; batch shortened to 32):
+    size-independent properties instead of an oracle run.
+      * softmax rows sum to 1: with V == 1 the output is exactly 1 (to rounding);
+      * linearity in V: attn(q,k,a*v1 + v2) == a*attn(q,k,v1) + attn(q,k,v2);
+      * lse is the log-sum-exp: re-deriving one row on the host matches."""
+    b, h, n, d = 32, 12, 197, 64
+    mode, param, grid, bias_np = _bias_case(kind, h, n)
+    prm = None if param is None else param.to(DEV)
+    planes = _planes(b, h, n, d, dtype, seed=11).to(DEV)
+    scale = d ** -0.5
+    ones = planes.clone()
+    ones[2] = 1.0
+    out1 = ops.fused_attention(ones, scale, mode, prm, grid)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert (out1.float() - 1.0).abs().max().item() <= tol
+    v2 = _planes(b, h, n, d, dtype, seed=12)[2].to(DEV)
+    pa, pb, pc = planes.clone(), planes.clone(), planes.clone()
+    pb[2] = v2
+    pc[2] = (0.5 * planes[2].float() + v2.float()).to(dtype)
+    oa, ob, oc = (ops.fused_attention(p_, scale, mode, prm, grid).float() for p_ in (pa, pb, pc))
+    lin_tol = 2e-5 if dtype == torch.float32 else 4e-2
+    assert (oc - (0.5 * oa + ob)).abs().max().item() <= lin_tol
+    # one row re-derived in float64
+    pl = planes[:, 3, 5].double().cpu().numpy()  # [3, N, D]
+    s = pl[0] @ pl[1].T * scale + (0 if bias_np is None else bias_np[5])
+    p_ = np.exp(s - s.max(-1, keepdims=True))
+    o_row = (p_ / p_.sum(-1, keepdims=True)) @ pl[2]
+    got = oa[3].reshape(n, h, d)[:, 5].double().cpu().numpy()
+    e = np.abs(got - o_row).max() / max(1.0, np.abs(o_row).max())
+    assert e <= (FP32_TOL if dtype == torch.float32 else BF16_TOL)

@@ -1,0 +1,45 @@
+// Internal kernel-launcher declarations shared by the translation units of libvrr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/vrr.h"
+
+namespace vrr {
+
+// attn_simt.cu
+int attn_fwd_simt(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
+                  int Dh, float scale, int dtype, cudaStream_t st);
+int attn_bwd_simt(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out,
+                  const float* lse, void* d_planes, float* d_bias_param, float* delta, float* d_lut_ws, int B,
+                  int H, int N, int Dh, float scale, int dtype, cudaStream_t st);
+
+// attn_tc.cu (tcgen05 / TMEM, bf16, Dh == 64)
+bool attn_fwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
+int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
+                int Dh, float scale, cudaStream_t st);
+
+// gemm_simt.cu
+int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
+                      int B, int N, int E, int H, int rope_mode, int dtype, cudaStream_t st);
+int gemm_simt(const void* a, const void* b, void* c, int M, int N, int K, int ta, int tb, int dtype,
+              int c_dtype, cudaStream_t st);
+int patch_embed_fwd_simt(const void* images, const void* weight, const void* bias, const void* cls,
+                         const void* pos, void* tokens, int B, int C, int Hi, int Wi, int P, int E, int dtype,
+                         int tok_dtype, cudaStream_t st);
+int patch_embed_bwd_simt(const void* images, const void* d_tokens, float* d_weight, float* d_bias, float* d_cls,
+                         float* d_pos, int B, int C, int Hi, int Wi, int P, int E, int dtype, int tok_dtype,
+                         cudaStream_t st);
+
+// gemm_tc.cu (tcgen05 / TMEM / TMA, bf16)
+bool qkv_rope_fwd_tc_supported(int B, int N, int E, int H);
+int qkv_rope_fwd_tc(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
+                    int B, int N, int E, int H, int rope_mode, cudaStream_t st);
+
+// rope.cu
+int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,
+                 void* d_qkv, float* d_cos, float* d_sin, int B, int N, int E, int H, int rope_mode, int dtype,
+                 cudaStream_t st);
+int rope_apply(const void* q_in, const void* k_in, const float* cos_tab, const float* sin_tab, void* q_out,
+               void* k_out, int B, int H, int Nr, int Dh, int rope_mode, int inverse, int dtype, cudaStream_t st);
+
+}  // namespace vrr

@@ -1,0 +1,217 @@
+// extern "C" entry points of libvrr_b200.so (see include/vrr.h): argument validation, kernel
+// family selection, workspace carving.  No allocation, no synchronisation, no exceptions.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vrr {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_impl{VRR_IMPL_AUTO};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_dev_checked = -1;  // -1 unknown, 0 bad, 1 ok (per process; one device per process)
+static int g_sms = 148;
+
+int require_device() {
+  if (g_dev_checked == 1) return VRR_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return VRR_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return VRR_ERR_NO_DEVICE;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libvrr_b200 is built for sm_100a only (no fallback path)", dev,
+              prop.major, prop.minor);
+    g_dev_checked = 0;
+    return VRR_ERR_NO_DEVICE;
+  }
+  g_sms = prop.multiProcessorCount;
+  g_dev_checked = 1;
+  return VRR_OK;
+}
+int sm_count() { return g_sms; }
+
+static bool dtype_ok(int d) { return d == VRR_F32 || d == VRR_BF16; }
+static bool dh_ok(int dh) { return dh == 16 || dh == 32 || dh == 64; }
+
+static int check_bias(const vrr_bias_desc* b, int H, int N) {
+  if (!b || b->mode == VRR_BIAS_NONE) return VRR_OK;
+  VRR_REQUIRE(b->param != nullptr, VRR_ERR_INVALID_ARG, "bias: param is NULL");
+  if (b->mode == VRR_BIAS_TABLE) {
+    VRR_REQUIRE(b->heads == H && b->len == 2 * N - 1, VRR_ERR_INVALID_ARG,
+                "bias table must be [H=%d][2N-1=%d], got [%d][%d] (the relative table is tied to the "
+                "construction-time token count)", H, 2 * N - 1, b->heads, b->len);
+  } else if (b->mode == VRR_BIAS_POLY) {
+    VRR_REQUIRE((b->heads == 1 || b->heads == H) && b->len >= 1 && b->len <= 16, VRR_ERR_INVALID_ARG,
+                "poly coefficients must be [1 or H][1..16], got [%d][%d]", b->heads, b->len);
+    VRR_REQUIRE(b->grid >= 1 && b->grid * b->grid == N - 1, VRR_ERR_INVALID_ARG,
+                "poly bias needs N-1 == grid^2 (N=%d, grid=%d)", N, b->grid);
+  } else {
+    set_error("bias: unknown mode %d", b->mode);
+    return VRR_ERR_INVALID_ARG;
+  }
+  return VRR_OK;
+}
+
+}  // namespace vrr
+
+using namespace vrr;
+
+extern "C" {
+
+int vrr_abi_version(void) { return VRR_ABI_VERSION; }
+const char* vrr_last_error(void) { return g_err; }
+int vrr_device_ok(void) { return require_device() == VRR_OK ? 1 : 0; }
+int vrr_set_impl(int impl) {
+  if (impl < VRR_IMPL_AUTO || impl > VRR_IMPL_TCGEN05) return g_impl.load();
+  return g_impl.exchange(impl);
+}
+uint64_t vrr_launch_count(void) { return g_launches.load(); }
+
+int vrr_patch_embed_fwd(const void* images, const void* weight, const void* bias, const void* cls_token,
+                        const void* pos_embed, void* tokens, int B, int C, int Hi, int Wi, int P, int E,
+                        int dtype, int tok_dtype, void* stream) {
+  VRR_REQUIRE(images && weight && bias && cls_token && tokens, VRR_ERR_INVALID_ARG, "patch_embed_fwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(tok_dtype), VRR_ERR_INVALID_ARG, "patch_embed_fwd: bad dtype %d/%d", dtype, tok_dtype);
+  VRR_REQUIRE(B > 0 && C > 0 && P > 0 && E > 0 && Hi >= P && Wi >= P, VRR_ERR_INVALID_ARG,
+              "patch_embed_fwd: bad sizes B=%d C=%d Hi=%d Wi=%d P=%d E=%d", B, C, Hi, Wi, P, E);
+  if (int rc = require_device()) return rc;
+  return patch_embed_fwd_simt(images, weight, bias, cls_token, pos_embed, tokens, B, C, Hi, Wi, P, E, dtype,
+                              tok_dtype, (cudaStream_t)stream);
+}
+
+int vrr_patch_embed_bwd(const void* images, const void* d_tokens, void* d_weight, void* d_bias, void* d_cls,
+                        void* d_pos, int B, int C, int Hi, int Wi, int P, int E, int dtype, int tok_dtype,
+                        void* stream) {
+  VRR_REQUIRE(images && d_tokens && d_weight && d_bias && d_cls, VRR_ERR_INVALID_ARG, "patch_embed_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(tok_dtype), VRR_ERR_INVALID_ARG, "patch_embed_bwd: bad dtype %d/%d", dtype, tok_dtype);
+  VRR_REQUIRE(B > 0 && C > 0 && P > 0 && E > 0 && Hi >= P && Wi >= P, VRR_ERR_INVALID_ARG,
+              "patch_embed_bwd: bad sizes");
+  if (int rc = require_device()) return rc;
+  return patch_embed_bwd_simt(images, d_tokens, (float*)d_weight, (float*)d_bias, (float*)d_cls, (float*)d_pos, B,
+                              C, Hi, Wi, P, E, dtype, tok_dtype, (cudaStream_t)stream);
+}
+
+int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, const float* sin_tab, void* planes,
+                     int B, int N, int E, int H, int rope_mode, int dtype, void* stream) {
+  VRR_REQUIRE(x && w_qkv && planes, VRR_ERR_INVALID_ARG, "qkv_rope_fwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "qkv_rope_fwd: bad dtype %d", dtype);
+  VRR_REQUIRE(rope_mode >= VRR_ROPE_NONE && rope_mode <= VRR_ROPE_MIXED, VRR_ERR_INVALID_ARG,
+              "qkv_rope_fwd: bad rope_mode %d", rope_mode);
+  VRR_REQUIRE(rope_mode == VRR_ROPE_NONE || (cos_tab && sin_tab), VRR_ERR_INVALID_ARG,
+              "qkv_rope_fwd: cos/sin required for rope_mode %d", rope_mode);
+  VRR_REQUIRE(B > 0 && N > 0 && H > 0 && E > 0 && E % H == 0, VRR_ERR_INVALID_ARG, "qkv_rope_fwd: bad sizes");
+  VRR_REQUIRE(dh_ok(E / H), VRR_ERR_UNSUPPORTED, "qkv_rope_fwd: head dim %d unsupported (16, 32, 64)", E / H);
+  if (int rc = require_device()) return rc;
+  const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && qkv_rope_fwd_tc_supported(B, N, E, H))
+    return qkv_rope_fwd_tc(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
+  VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
+              "qkv_rope_fwd: tcgen05 kernel forced but shape/dtype unsupported (bf16, Dh=64, E%%64==0)");
+  return qkv_rope_fwd_simt(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, dtype, (cudaStream_t)stream);
+}
+
+int vrr_qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,
+                     void* d_qkv, float* d_cos, float* d_sin, int B, int N, int E, int H, int rope_mode,
+                     int dtype, void* stream) {
+  VRR_REQUIRE(d_planes && planes && d_qkv, VRR_ERR_INVALID_ARG, "qkv_rope_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "qkv_rope_bwd: bad dtype %d", dtype);
+  VRR_REQUIRE(rope_mode >= VRR_ROPE_NONE && rope_mode <= VRR_ROPE_MIXED, VRR_ERR_INVALID_ARG,
+              "qkv_rope_bwd: bad rope_mode %d", rope_mode);
+  VRR_REQUIRE(rope_mode == VRR_ROPE_NONE || (cos_tab && sin_tab), VRR_ERR_INVALID_ARG,
+              "qkv_rope_bwd: cos/sin required");
+  VRR_REQUIRE((d_cos == nullptr) == (d_sin == nullptr), VRR_ERR_INVALID_ARG,
+              "qkv_rope_bwd: d_cos and d_sin must both be given or both NULL");
+  VRR_REQUIRE(B > 0 && N > 0 && H > 0 && E > 0 && E % H == 0 && dh_ok(E / H), VRR_ERR_INVALID_ARG,
+              "qkv_rope_bwd: bad sizes");
+  if (int rc = require_device()) return rc;
+  return qkv_rope_bwd(d_planes, planes, cos_tab, sin_tab, d_qkv, d_cos, d_sin, B, N, E, H, rope_mode, dtype,
+                      (cudaStream_t)stream);
+}
+
+int vrr_rope_apply(const void* q_in, const void* k_in, const float* cos_tab, const float* sin_tab, void* q_out,
+                   void* k_out, int B, int H, int Nr, int Dh, int rope_mode, int inverse, int dtype,
+                   void* stream) {
+  VRR_REQUIRE(q_in && k_in && cos_tab && sin_tab && q_out && k_out, VRR_ERR_INVALID_ARG, "rope_apply: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "rope_apply: bad dtype %d", dtype);
+  VRR_REQUIRE(rope_mode == VRR_ROPE_AXIAL || rope_mode == VRR_ROPE_MIXED, VRR_ERR_INVALID_ARG,
+              "rope_apply: bad rope_mode %d", rope_mode);
+  VRR_REQUIRE(B > 0 && H > 0 && Nr > 0 && Dh > 0 && Dh % 2 == 0, VRR_ERR_INVALID_ARG, "rope_apply: bad sizes");
+  if (int rc = require_device()) return rc;
+  return rope_apply(q_in, k_in, cos_tab, sin_tab, q_out, k_out, B, H, Nr, Dh, rope_mode, inverse, dtype,
+                    (cudaStream_t)stream);
+}
+
+int vrr_gemm(const void* a, const void* b, void* c, int M, int N, int K, int trans_a, int trans_b, int dtype,
+             int c_dtype, void* stream) {
+  VRR_REQUIRE(a && b && c, VRR_ERR_INVALID_ARG, "gemm: NULL pointer");
+  VRR_REQUIRE(M > 0 && N > 0 && K > 0, VRR_ERR_INVALID_ARG, "gemm: bad sizes");
+  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(c_dtype), VRR_ERR_INVALID_ARG, "gemm: bad dtype %d/%d", dtype, c_dtype);
+  if (int rc = require_device()) return rc;
+  return gemm_simt(a, b, c, M, N, K, trans_a, trans_b, dtype, c_dtype, (cudaStream_t)stream);
+}
+
+int vrr_attn_fwd(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
+                 int Dh, float scale, int dtype, void* stream) {
+  VRR_REQUIRE(planes && out && lse, VRR_ERR_INVALID_ARG, "attn_fwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "attn_fwd: bad dtype %d", dtype);
+  VRR_REQUIRE(B > 0 && H > 0 && N > 0, VRR_ERR_INVALID_ARG, "attn_fwd: bad sizes");
+  VRR_REQUIRE(dh_ok(Dh), VRR_ERR_UNSUPPORTED, "attn_fwd: head dim %d unsupported (16, 32, 64)", Dh);
+  if (int rc = check_bias(bias, H, N)) return rc;
+  if (int rc = require_device()) return rc;
+  const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_fwd_tc_supported(B, H, N, Dh, bias))
+    return attn_fwd_tc(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
+  VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
+              "attn_fwd: tcgen05 kernel forced but shape/dtype unsupported (bf16, Dh=64)");
+  return attn_fwd_simt(planes, bias, out, lse, B, H, N, Dh, scale, dtype, (cudaStream_t)stream);
+}
+
+size_t vrr_attn_bwd_workspace_bytes(int B, int H, int N, int Dh, const vrr_bias_desc* bias) {
+  (void)Dh;
+  size_t delta = (size_t)B * H * N * sizeof(float);
+  size_t lut = (size_t)H * (size_t)bias_lut_len(bias, N) * sizeof(float);
+  return ((delta + 255) / 256) * 256 + ((lut + 255) / 256) * 256 + 256;
+}
+
+int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out,
+                 const float* lse, void* d_planes, float* d_bias_param, void* workspace, size_t workspace_bytes,
+                 int B, int H, int N, int Dh, float scale, int dtype, void* stream) {
+  VRR_REQUIRE(planes && out && d_out && lse && d_planes && workspace, VRR_ERR_INVALID_ARG, "attn_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "attn_bwd: bad dtype %d", dtype);
+  VRR_REQUIRE(B > 0 && H > 0 && N > 0, VRR_ERR_INVALID_ARG, "attn_bwd: bad sizes");
+  VRR_REQUIRE(dh_ok(Dh), VRR_ERR_UNSUPPORTED, "attn_bwd: head dim %d unsupported (16, 32, 64)", Dh);
+  if (int rc = check_bias(bias, H, N)) return rc;
+  const bool has_bias = bias && bias->mode != VRR_BIAS_NONE;
+  VRR_REQUIRE(!has_bias || d_bias_param, VRR_ERR_INVALID_ARG, "attn_bwd: d_bias_param required with a bias");
+  VRR_REQUIRE(workspace_bytes >= vrr_attn_bwd_workspace_bytes(B, H, N, Dh, bias), VRR_ERR_WORKSPACE,
+              "attn_bwd: workspace %zu < %zu bytes", workspace_bytes, vrr_attn_bwd_workspace_bytes(B, H, N, Dh, bias));
+  VRR_REQUIRE(((uintptr_t)workspace & 255) == 0, VRR_ERR_INVALID_ARG, "attn_bwd: workspace must be 256-byte aligned");
+  if (int rc = require_device()) return rc;
+  float* delta = (float*)workspace;
+  size_t delta_bytes = (((size_t)B * H * N * sizeof(float) + 255) / 256) * 256;
+  float* d_lut = (float*)((char*)workspace + delta_bytes);
+  return attn_bwd_simt(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, d_lut, B, H, N, Dh, scale,
+                       dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Vision Transformer: drop-in for ``models/vit.py`` of the reference, running the attention hot
+path on the sm_100a kernels of ``libvrr_b200``.
+
+``Attention`` / ``Block`` / ``VisionTransformer`` keep the reference's constructor and ``forward``
+signatures, attribute names, sub-module names (hence ``state_dict`` keys, including the per-block
+``attn.pos_encoding.*`` duplicates of the shared PE module) and RNG consumption order at
+construction (citations: /root/reference/models/vit.py).  What changes is underneath:
+
+* patch embedding + cls concat + absolute add      -> one unfold+GEMM kernel   (vit.py:248-258)
+* qkv Linear + head split + RoPE + cls re-concat    -> one GEMM with RoPE epilogue (vit.py:47-68)
+* QK^T, scale, RPE / Poly-RPE bias, softmax, PV, merge -> one fused attention kernel (vit.py:71-88)
+
+LayerNorm, the output projection, the MLP and the head stay ``torch.nn`` (SURVEY.md section 8(f) rows
+N1-N3: next).  CUDA sm_100 only: CPU inputs raise; there is no fallback path.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from .positional_encoding import (AbsolutePositionalEncoding, NoPositionalEncoding, PolynomialRPE,
+                                  RelativePositionalEncoding, RoPEAxial, RoPEMixed)
+
+
+class Mlp(nn.Module):
+    """fc1 -> GELU -> fc2 with timm's parameter names (the reference takes it from timm, vit.py:9,118)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        hidden_features = hidden_features or in_features
+        out_features = out_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop)
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop2 = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop2(self.fc2(self.drop1(self.act(self.fc1(x)))))
+
+
+class Attention(nn.Module):
+    """Multi-head self-attention (reference vit.py:14-98) on the fused kernels."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        if qkv_bias:
+            raise NotImplementedError("qkv_bias=True is never used by the reference (vit.py:110,200) and the "
+                                      "fused QKV+RoPE kernel has no bias term")
+        if attn_drop != 0.:
+            raise NotImplementedError("attention dropout is structurally 0 in the reference (vit.py:110,200); "
+                                      "the fused attention kernel has no dropout")
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.pos_encoding = None
+
+    def forward(self, x, freqs_cis=None):
+        pe = self.pos_encoding
+        cos = sin = None
+        bias_mode, bias_param, bias_grid = _lib.BIAS_NONE, None, 0
+        if isinstance(pe, (RoPEAxial, RoPEMixed)) and freqs_cis is not None:
+            cos, sin = freqs_cis  # rotary branch: no additive bias (vit.py:51-71)
+        elif isinstance(pe, RelativePositionalEncoding):
+            bias_mode, bias_param = _lib.BIAS_TABLE, pe.relative_position_bias_table
+        elif isinstance(pe, PolynomialRPE):
+            bias_mode, bias_param, bias_grid = _lib.BIAS_POLY, pe.coefficients, pe.grid_size
+        planes = ops.qkv_rope(x, self.qkv.weight, cos, sin, self.num_heads)
+        out = ops.fused_attention(planes, self.scale, bias_mode, bias_param, bias_grid)
+        return self.proj_drop(self.proj(out))
+
+    def set_pos_encoding(self, pos_encoding):
+        self.pos_encoding = pos_encoding  # registers the shared PE module as a child (state_dict dups)
+
+
+class Block(nn.Module):
+    """Pre-LN transformer block (reference vit.py:100-129)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, drop=0., attn_drop=0.,
+                 drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if drop_path > 0.:
+            raise NotImplementedError("drop_path is always 0 in the reference (vit.py:200)")
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def forward(self, x, freqs_cis=None):
+        x = x + self.drop_path(self.attn(self.norm1(x), freqs_cis=freqs_cis))
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x
+
+    def set_pos_encoding(self, pos_encoding):
+        self.attn.set_pos_encoding(pos_encoding)
+
+
+class VisionTransformer(nn.Module):
+    """ViT with selectable positional encoding (reference vit.py:131-285).
+
+    ``pos_encoding`` is one of ``none | absolute | relative | polynomial | rope-axial | rope-mixed``;
+    anything else raises ``ValueError`` (vit.py:196).
+    """
+
+    def __init__(self, img_size=32, patch_size=4, in_chans=3, num_classes=10,
+                 embed_dim=192, depth=6, num_heads=6, mlp_ratio=4.,
+                 pos_encoding='absolute', rope_theta=100.0,
+                 poly_degree=3, poly_shared_heads=True):
+        super().__init__()
+        self.num_classes = num_classes
+        self.embed_dim = embed_dim
+        self.patch_size = patch_size
+        self.pos_encoding_type = pos_encoding
+        self.head_dim = embed_dim // num_heads
+        self.num_heads = num_heads
+        self.num_patches = (img_size // patch_size) ** 2
+
+        # parameter holder for the patch projection; the forward pass runs the unfold+GEMM kernel
+        self.patch_embed = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+
+        self.use_pos_embed_in_forward = pos_encoding == 'absolute'
+        self.use_rope = pos_encoding in ('rope-axial', 'rope-mixed')
+        if pos_encoding == 'absolute':
+            self.pos_embed = AbsolutePositionalEncoding(embed_dim)
+        elif pos_encoding == 'relative':
+            self.pos_embed = RelativePositionalEncoding(self.num_patches, num_heads)
+        elif pos_encoding == 'polynomial':
+            self.pos_embed = PolynomialRPE(self.num_patches, degree=poly_degree, num_heads=num_heads,
+                                           shared_across_heads=poly_shared_heads)
+        elif pos_encoding == 'rope-axial':
+            self.pos_embed = RoPEAxial(dim=self.head_dim, theta=rope_theta)
+        elif pos_encoding == 'rope-mixed':
+            self.pos_embed = RoPEMixed(dim=self.head_dim, num_heads=num_heads, theta=rope_theta)
+        elif pos_encoding == 'none':
+            self.pos_embed = NoPositionalEncoding()
+        else:
+            raise ValueError(f"Unknown positional encoding type: {pos_encoding}")
+
+        self.blocks = nn.ModuleList([Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
+        if not self.use_pos_embed_in_forward:
+            for blk in self.blocks:
+                blk.set_pos_encoding(self.pos_embed)  # one shared module, referenced by every block
+
+        self.norm = nn.LayerNorm(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        """Same initialisers as the reference (vit.py:216-233); PE parameters are left alone."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+        elif isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def forward_features(self, x):
+        """[B, C, H, W] -> [B, N, E] with N = (H/P)(W/P) + 1 taken from the input (vit.py:235-271)."""
+        B, C, H, W = x.shape
+        h, w = H // self.patch_size, W // self.patch_size
+        abs_table = self.pos_embed.pos_embed if self.use_pos_embed_in_forward else None
+        # (under autocast the token stream comes back fp32, like the reference's cat with the fp32 cls token)
+        x = ops.patch_embed(x, self.patch_embed.weight, self.patch_embed.bias, self.cls_token,
+                            abs_table, self.patch_size)
+
+        freqs_cis = None
+        if self.use_rope:
+            freqs_cis = self.pos_embed.get_freqs_cis(h * w, x.device)  # once per forward, all blocks
+        for blk in self.blocks:
+            x = blk(x, freqs_cis=freqs_cis)
+        return x
+
+    def forward(self, x):
+        x = self.forward_features(x)
+        x = self.norm(x)
+        return self.head(x[:, 0])

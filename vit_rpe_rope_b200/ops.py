@@ -1,0 +1,324 @@
+"""Autograd bindings of the libvrr_b200 kernels (host side of the C ABI).
+
+Each ``torch.autograd.Function`` here is the product implementation of one stretch of the
+reference's ``Attention.forward`` / ``forward_features`` (citations: /root/reference):
+
+* :class:`PatchEmbedFn`      - models/vit.py:164,248-258 (conv patch embed, cls concat, absolute add)
+* :class:`QkvRopeFn`         - models/vit.py:47-68 + models/rope_utils.py:22-35
+* :class:`FusedAttentionFn`  - models/vit.py:71-88
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic on these
+paths runs in the hand-written sm_100a kernels.  CUDA only - CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.VRR_F32, torch.bfloat16: _lib.VRR_BF16}
+
+
+def compute_dtype(x: torch.Tensor) -> torch.dtype:
+    """Element type the kernels run in: the autocast dtype inside ``torch.autocast('cuda')``
+    (how the build defines "bf16 training"), else the tensor's own dtype."""
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    if dt not in _DT:
+        raise TypeError(f"vit_rpe_rope_b200 kernels support float32 and bfloat16, got {dt}")
+    return dt
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "vit_rpe_rope_b200 runs on CUDA sm_100 devices only (no CPU fallback); got a "
+                f"{t.device} tensor")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+# bench.py sets this to a list to time individual kernel launches with CUDA events recorded on the
+# launching (current) stream; None (default) adds no overhead.
+PROFILE_EVENTS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE_EVENTS is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if PROFILE_EVENTS is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE_EVENTS.append((self.name, self.start, end))
+        return False
+
+
+# ------------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """tokens[B, Np+1, E] from images: unfold + GEMM + bias (+ absolute pos_embed) + cls row.
+
+    images / weight / bias share the conv dtype; cls_token / pos_embed / tokens share the token-stream
+    dtype (fp32 under autocast, like the reference's cat with the fp32 cls token)."""
+
+    @staticmethod
+    def forward(ctx, images, weight, bias, cls_token, pos_embed, patch):
+        _require_cuda(images, weight, bias, cls_token, pos_embed)
+        lib = _lib.load()
+        B, C, Hi, Wi = images.shape
+        E = weight.shape[0]
+        dt, tdt = images.dtype, cls_token.dtype
+        if weight.dtype != dt or bias.dtype != dt or (pos_embed is not None and pos_embed.dtype != tdt):
+            raise TypeError("patch_embed: images/weight/bias must share a dtype, cls_token/pos_embed another")
+        images = images.contiguous()
+        w = weight.detach().contiguous()
+        b = bias.detach().contiguous()
+        cls = cls_token.detach().reshape(-1).contiguous()
+        Np = (Hi // patch) * (Wi // patch)
+        pos = None
+        if pos_embed is not None:
+            if pos_embed.shape[-2] < Np:
+                raise RuntimeError(f"absolute pos_embed has {pos_embed.shape[-2]} rows, need {Np}")
+            pos = pos_embed.detach().reshape(-1, E).contiguous()
+        tokens = torch.empty(B, Np + 1, E, device=images.device, dtype=tdt)
+        with torch.cuda.device(images.device):
+            _lib.check(lib.vrr_patch_embed_fwd(_ptr(images), _ptr(w), _ptr(b), _ptr(cls), _ptr(pos),
+                                               _ptr(tokens), B, C, Hi, Wi, patch, E, _DT[dt], _DT[tdt],
+                                               _stream()), "vrr_patch_embed_fwd")
+        ctx.save_for_backward(images)
+        ctx.meta = (B, C, Hi, Wi, patch, E, Np, pos_embed.shape if pos_embed is not None else None,
+                    weight.shape, cls_token.shape, dt, tdt)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, d_tokens):
+        lib = _lib.load()
+        (images,) = ctx.saved_tensors
+        B, C, Hi, Wi, patch, E, Np, pos_shape, w_shape, cls_shape, dt, tdt = ctx.meta
+        d_tokens = d_tokens.contiguous()
+        dev = images.device
+        d_w = torch.empty(E, C * patch * patch, device=dev, dtype=torch.float32)
+        d_b = torch.empty(E, device=dev, dtype=torch.float32)
+        d_cls = torch.empty(E, device=dev, dtype=torch.float32)
+        d_pos_rows = torch.empty(Np, E, device=dev, dtype=torch.float32) if pos_shape is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.vrr_patch_embed_bwd(_ptr(images), _ptr(d_tokens), _ptr(d_w), _ptr(d_b), _ptr(d_cls),
+                                               _ptr(d_pos_rows), B, C, Hi, Wi, patch, E, _DT[dt], _DT[tdt],
+                                               _stream()), "vrr_patch_embed_bwd")
+        d_pos = None
+        if pos_shape is not None:
+            d_pos = torch.zeros(pos_shape, device=dev, dtype=tdt)
+            d_pos.view(-1, E)[:Np] = d_pos_rows.to(tdt)
+        return (None, d_w.view(w_shape).to(dt), d_b.to(dt), d_cls.view(cls_shape).to(tdt), d_pos, None)
+
+
+def patch_embed(images, weight, bias, cls_token, pos_embed, patch):
+    """Conv operands are cast to the compute dtype (autograd-tracked casts keep fp32 master grads);
+    under autocast the token stream (cls, pos, output) stays fp32 as in the reference."""
+    dt = compute_dtype(images)
+    tdt = torch.float32 if torch.is_autocast_enabled("cuda") else dt
+    return PatchEmbedFn.apply(images.to(dt), weight.to(dt), bias.to(dt), cls_token.to(tdt),
+                              None if pos_embed is None else pos_embed.to(tdt), patch)
+
+
+# ------------------------------------------------------------------------------------------------
+def _rope_args(cos, sin, H, N, Dh):
+    """Classify the (cos, sin) pair the way ``reshape_for_broadcast`` does (rope_utils.py:39-66)."""
+    if cos is None:
+        return _lib.ROPE_NONE
+    if cos.shape != sin.shape:
+        raise RuntimeError(f"cos {tuple(cos.shape)} and sin {tuple(sin.shape)} differ")
+    if cos.ndim == 2:
+        mode, want = _lib.ROPE_AXIAL, (N - 1, Dh // 2)
+    elif cos.ndim == 3:
+        mode, want = _lib.ROPE_MIXED, (H, N - 1, Dh // 2)
+    else:
+        raise ValueError(f"Unexpected tensor shapes: {cos.shape} vs {(1, H, N - 1, Dh)}")
+    if tuple(cos.shape) != want:
+        raise RuntimeError(f"RoPE table shape {tuple(cos.shape)} does not broadcast against the "
+                           f"{N - 1} patch tokens x {H} heads x {Dh} channels (expected {want})")
+    return mode
+
+
+class QkvRopeFn(torch.autograd.Function):
+    """planes[3, B, H, N, Dh] = split_heads(x @ w_qkv^T), q/k rows 1.. rotated in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w_qkv, cos, sin, num_heads):
+        _require_cuda(x, w_qkv, cos, sin)
+        lib = _lib.load()
+        B, N, E = x.shape
+        H, Dh = num_heads, E // num_heads
+        mode = _rope_args(cos, sin, H, N, Dh)
+        x = x.contiguous()
+        w = w_qkv.detach().contiguous()
+        cos32, sin32 = _f32c(cos), _f32c(sin)
+        planes = torch.empty(3, B, H, N, Dh, device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device), _timed("qkv_rope_fwd"):
+            _lib.check(lib.vrr_qkv_rope_fwd(_ptr(x), _ptr(w), _ptr(cos32), _ptr(sin32), _ptr(planes), B, N, E, H,
+                                            mode, _DT[x.dtype], _stream()), "vrr_qkv_rope_fwd")
+        ctx.save_for_backward(x, w, planes, cos32, sin32)
+        ctx.meta = (B, N, E, H, mode, None if cos is None else (cos.dtype, sin.dtype))
+        return planes
+
+    @staticmethod
+    def backward(ctx, d_planes):
+        lib = _lib.load()
+        x, w, planes, cos32, sin32 = ctx.saved_tensors
+        B, N, E, H, mode, cs_dtypes = ctx.meta
+        d_planes = d_planes.contiguous()
+        dev, dt = x.device, x.dtype
+        need_cs = mode != _lib.ROPE_NONE and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        d_cos = torch.empty_like(cos32) if need_cs else None
+        d_sin = torch.empty_like(sin32) if need_cs else None
+        d_qkv = torch.empty(B * N, 3 * E, device=dev, dtype=dt)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vrr_qkv_rope_bwd(_ptr(d_planes), _ptr(planes), _ptr(cos32), _ptr(sin32), _ptr(d_qkv),
+                                            _ptr(d_cos), _ptr(d_sin), B, N, E, H, mode, _DT[dt], _stream()),
+                       "vrr_qkv_rope_bwd")
+            dx = dw = None
+            if ctx.needs_input_grad[0]:
+                dx = _gemm(d_qkv, w, False, False, dt).view(B, N, E)          # [BN,3E] . [3E,E]
+            if ctx.needs_input_grad[1]:
+                dw = _gemm(d_qkv, x.view(B * N, E), True, False, dt)          # [3E,BN] . [BN,E]
+        if need_cs:
+            d_cos, d_sin = d_cos.to(cs_dtypes[0]), d_sin.to(cs_dtypes[1])
+        return dx, dw, d_cos, d_sin, None
+
+
+def _gemm(a, b, trans_a, trans_b, out_dtype):
+    """Plain projection-backward GEMM.  fp32: the library's FFMA kernel (exact fp32 products, no
+    TF32).  bf16: cuBLAS through torch.matmul - a plain library GEMM with no fused work, which the
+    build rules allow; fp32 accumulation, bf16 result."""
+    if a.dtype == torch.float32:
+        lib = _lib.load()
+        M = a.shape[1] if trans_a else a.shape[0]
+        K = a.shape[0] if trans_a else a.shape[1]
+        N = b.shape[0] if trans_b else b.shape[1]
+        c = torch.empty(M, N, device=a.device, dtype=torch.float32)
+        _lib.check(lib.vrr_gemm(_ptr(a), _ptr(b), _ptr(c), M, N, K, int(trans_a), int(trans_b), _lib.VRR_F32,
+                                _lib.VRR_F32, _stream()), "vrr_gemm")
+        return c.to(out_dtype)
+    with torch.autocast("cuda", enabled=False):
+        return torch.matmul(a.t() if trans_a else a, b.t() if trans_b else b)
+
+
+def qkv_rope(x, w_qkv, cos, sin, num_heads):
+    dt = compute_dtype(x)
+    return QkvRopeFn.apply(x.to(dt), w_qkv.to(dt), cos, sin, num_heads)
+
+
+# ------------------------------------------------------------------------------------------------
+class FusedAttentionFn(torch.autograd.Function):
+    """out[B, N, E] = merge_heads(softmax(q k^T * scale + bias) v) from the qkv planes."""
+
+    @staticmethod
+    def forward(ctx, planes, bias_param, bias_mode, bias_grid, scale):
+        _require_cuda(planes, bias_param)
+        lib = _lib.load()
+        _, B, H, N, Dh = planes.shape
+        planes = planes.contiguous()
+        bp = _f32c(bias_param)
+        desc = _bias_desc(bias_mode, bp, bias_grid)
+        out = torch.empty(B, N, H * Dh, device=planes.device, dtype=planes.dtype)
+        lse = torch.empty(B, H, N, device=planes.device, dtype=torch.float32)
+        with torch.cuda.device(planes.device), _timed("attn_fwd"):
+            _lib.check(lib.vrr_attn_fwd(_ptr(planes), ctypes.byref(desc), _ptr(out), _ptr(lse), B, H, N, Dh,
+                                        float(scale), _DT[planes.dtype], _stream()), "vrr_attn_fwd")
+        ctx.save_for_backward(planes, out, lse, bp)
+        ctx.meta = (B, H, N, Dh, float(scale), bias_mode, bias_grid,
+                    None if bias_param is None else (bias_param.shape, bias_param.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        planes, out, lse, bp = ctx.saved_tensors
+        B, H, N, Dh, scale, bias_mode, bias_grid, bp_meta = ctx.meta
+        d_out = d_out.contiguous()
+        dev = planes.device
+        desc = _bias_desc(bias_mode, bp, bias_grid)
+        d_planes = torch.empty_like(planes)
+        d_bp = torch.empty_like(bp) if bp is not None else None
+        ws_bytes = int(lib.vrr_attn_bwd_workspace_bytes(B, H, N, Dh, ctypes.byref(desc)))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev), _timed("attn_bwd"):
+            _lib.check(lib.vrr_attn_bwd(_ptr(planes), ctypes.byref(desc), _ptr(out), _ptr(d_out), _ptr(lse),
+                                        _ptr(d_planes), _ptr(d_bp), _ptr(ws), ws_bytes, B, H, N, Dh, scale,
+                                        _DT[planes.dtype], _stream()), "vrr_attn_bwd")
+        if d_bp is not None:
+            d_bp = d_bp.view(bp_meta[0]).to(bp_meta[1])
+        return d_planes, d_bp, None, None, None
+
+
+def _bias_desc(mode, param32, grid):
+    d = _lib.BiasDesc()
+    d.mode = mode
+    if mode == _lib.BIAS_NONE:
+        d.heads = d.len = d.grid = 0
+        d.param = None
+        return d
+    p2 = param32.reshape(-1, param32.shape[-1])
+    d.heads, d.len, d.grid = p2.shape[0], p2.shape[1], int(grid)
+    d.param = param32.data_ptr()
+    return d
+
+
+def fused_attention(planes, scale, bias_mode=_lib.BIAS_NONE, bias_param=None, bias_grid=0):
+    return FusedAttentionFn.apply(planes, bias_param, bias_mode, bias_grid, scale)
+
+
+# ------------------------------------------------------------------------------------------------
+class RopeApplyFn(torch.autograd.Function):
+    """Stand-alone rotate-half of q and k (public ``apply_rotary_emb``, rope_utils.py:3-37)."""
+
+    @staticmethod
+    def forward(ctx, q, k, cos, sin):
+        _require_cuda(q, k, cos, sin)
+        lib = _lib.load()
+        B, H, Nr, Dh = q.shape
+        cos_b = torch.broadcast_to(cos, (1, cos.shape[1], Nr, Dh // 2))[0] if cos.ndim == 4 else cos
+        sin_b = torch.broadcast_to(sin, (1, sin.shape[1], Nr, Dh // 2))[0] if sin.ndim == 4 else sin
+        if cos_b.ndim == 3 and cos_b.shape[0] == 1:
+            cos_b, sin_b = cos_b[0], sin_b[0]
+        mode = _lib.ROPE_AXIAL if cos_b.ndim == 2 else _lib.ROPE_MIXED
+        want = (Nr, Dh // 2) if mode == _lib.ROPE_AXIAL else (H, Nr, Dh // 2)
+        if tuple(cos_b.shape) != want or tuple(sin_b.shape) != want:
+            raise RuntimeError(f"cos/sin {tuple(cos.shape)} do not broadcast against q {tuple(q.shape)}")
+        q, k = q.contiguous(), k.contiguous()
+        c32, s32 = _f32c(cos_b), _f32c(sin_b)
+        qo, ko = torch.empty_like(q), torch.empty_like(k)
+        with torch.cuda.device(q.device):
+            _lib.check(lib.vrr_rope_apply(_ptr(q), _ptr(k), _ptr(c32), _ptr(s32), _ptr(qo), _ptr(ko), B, H, Nr, Dh,
+                                          mode, 0, _DT[q.dtype], _stream()), "vrr_rope_apply")
+        ctx.save_for_backward(c32, s32)
+        ctx.meta = (B, H, Nr, Dh, mode)
+        return qo, ko
+
+    @staticmethod
+    def backward(ctx, dq, dk):
+        lib = _lib.load()
+        c32, s32 = ctx.saved_tensors
+        B, H, Nr, Dh, mode = ctx.meta
+        dq, dk = dq.contiguous(), dk.contiguous()
+        gq, gk = torch.empty_like(dq), torch.empty_like(dk)
+        with torch.cuda.device(dq.device):
+            _lib.check(lib.vrr_rope_apply(_ptr(dq), _ptr(dk), _ptr(c32), _ptr(s32), _ptr(gq), _ptr(gk), B, H, Nr,
+                                          Dh, mode, 1, _DT[dq.dtype], _stream()), "vrr_rope_apply")
+        return gq, gk, None, None
