@@ -73,8 +73,13 @@ def attention_forward(q, k, v, scale, bias=None, cos=None, sin=None):
     return o.transpose(0, 2, 1, 3).reshape(b, n, h * d), p, q, k
 
 
-def attention_backward(d_out, q, k, v, scale, bias=None, cos=None, sin=None):
+def attention_backward(d_out, q, k, v, scale, bias=None, cos=None, sin=None, out=None):
     """Gradient of :func:`attention_forward`.
+
+    ``out``: optionally the forward output [B, N, H*D] *as stored* (e.g. rounded to bf16).  The
+    row statistic ``delta = rowsum(dO * O)`` is then taken from it, which is what a backward pass
+    that re-reads the stored output computes (the reference's autograd does the equivalent with
+    its own stored softmax output).
 
     Returns a dict with ``dq, dk, dv`` [B,H,N,D] (w.r.t. the UN-rotated q, k),
     ``dbias`` [H,N,N] (sum over batch of dS), and for RoPE ``dcos, dsin`` with
@@ -84,6 +89,8 @@ def attention_backward(d_out, q, k, v, scale, bias=None, cos=None, sin=None):
     o, p, qr, kr = attention_forward(q0, k0, v, scale, bias, cos, sin)
     b, h, n, d = q0.shape
     do = np.asarray(d_out, np.float64).reshape(b, n, h, d).transpose(0, 2, 1, 3)
+    if out is not None:
+        o = np.asarray(out, np.float64)
     oh = o.reshape(b, n, h, d).transpose(0, 2, 1, 3)
     dv = np.einsum("bhij,bhid->bhjd", p, do)
     dp = np.einsum("bhid,bhjd->bhij", do, v)

@@ -3,7 +3,7 @@
 # Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -x --timeout=300 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 --timeout=300 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit: $?" >> gpurun_out/smoke.log
 for wl in vit-tiny-rope-axial-fp32 vit-tiny-polynomial-fp32 vitb16-224-rope-mixed-bf16; do

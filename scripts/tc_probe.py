@@ -1,0 +1,75 @@
+"""Cross-check the tcgen05 kernels against the SIMT kernels on a B200 (run under `timeout`).
+
+Prints one line per case with the max error relative to max|reference|; exits non-zero if any case
+is off.  Used by scripts/gpu_check.sh before the test-suite so that a broken tensor-core kernel is
+reported (and the run continues on the SIMT family) instead of hanging the suite."""
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vit_rpe_rope_b200 import _lib, ops  # noqa: E402
+
+dev = "cuda:0"
+which = sys.argv[1] if len(sys.argv) > 1 else "attn"
+bad = 0
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20)).item()
+
+
+if which == "attn":
+    cases = [(2, 3, n, kind) for n in (197, 65, 1, 16, 128, 129, 256, 257, 577, 1025) for kind in ("none", "table", "poly")]
+    cases += [(64, 12, 197, "none"), (64, 12, 197, "table"), (64, 12, 197, "poly"), (8, 16, 577, "none")]
+    for (b, h, n, kind) in cases:
+        g = int(round((n - 1) ** 0.5))
+        if kind == "poly" and (g * g != n - 1 or n == 1):
+            continue
+        gen = torch.Generator().manual_seed(n * 7 + b)
+        planes = (torch.randn(3, b, h, n, 64, generator=gen) * 0.8).to(torch.bfloat16).to(dev)
+        mode, prm, grid = _lib.BIAS_NONE, None, 0
+        if kind == "table":
+            mode, prm = _lib.BIAS_TABLE, (torch.randn(h, 2 * n - 1, generator=gen) * 0.5).to(dev)
+        elif kind == "poly":
+            mode, prm, grid = _lib.BIAS_POLY, (torch.randn(h, 4, generator=gen) * 0.02).to(dev), g
+        outs = {}
+        for name, impl in (("simt", _lib.IMPL_SIMT), ("tc", _lib.IMPL_TCGEN05)):
+            _lib.set_impl(impl)
+            o = ops.fused_attention(planes, 0.125, mode, prm, grid)
+            torch.cuda.synchronize()
+            outs[name] = o
+        e = rel(outs["tc"], outs["simt"])
+        ok = e < 2e-2 and bool(torch.isfinite(outs["tc"].float()).all())
+        bad += (not ok)
+        print(f"attn_fwd B={b} H={h} N={n} bias={kind}: rel err tc vs simt {e:.3e} {'ok' if ok else 'BAD'}", flush=True)
+elif which == "qkv":
+    for (b, n, e_, h, rope) in [(2, 197, 256, 4, "none"), (2, 197, 256, 4, "axial"), (2, 197, 256, 4, "mixed"),
+                                (3, 65, 192, 3, "mixed"), (1, 5, 64, 1, "axial"), (16, 197, 768, 12, "mixed"),
+                                (4, 577, 1024, 16, "axial"), (2, 1025, 768, 12, "mixed"), (7, 50, 128, 2, "none")]:
+        gen = torch.Generator().manual_seed(n + e_)
+        x = torch.randn(b, n, e_, generator=gen).to(torch.bfloat16).to(dev)
+        w = (torch.randn(3 * e_, e_, generator=gen) * e_ ** -0.5).to(torch.bfloat16).to(dev)
+        cos = sin = None
+        if rope != "none":
+            g = int(round((n - 1) ** 0.5))
+            if g * g != n - 1:
+                continue
+            dh = e_ // h
+            shape = (n - 1, dh // 2) if rope == "axial" else (h, n - 1, dh // 2)
+            ang = torch.rand(*shape, generator=gen) * 6.0
+            cos, sin = torch.cos(ang).to(dev), torch.sin(ang).to(dev)
+        outs = {}
+        for name, impl in (("simt", _lib.IMPL_SIMT), ("tc", _lib.IMPL_TCGEN05)):
+            _lib.set_impl(impl)
+            o = ops.QkvRopeFn.apply(x, w, cos, sin, h)
+            torch.cuda.synchronize()
+            outs[name] = o
+        er = rel(outs["tc"], outs["simt"])
+        ok = er < 2e-2 and bool(torch.isfinite(outs["tc"].float()).all())
+        bad += (not ok)
+        print(f"qkv_rope_fwd B={b} N={n} E={e_} H={h} rope={rope}: rel err tc vs simt {er:.3e} {'ok' if ok else 'BAD'}", flush=True)
+_lib.set_impl(_lib.IMPL_AUTO)
+print("PROBE", which, "FAILED" if bad else "PASSED", flush=True)
+sys.exit(1 if bad else 0)

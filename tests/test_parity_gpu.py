@@ -257,7 +257,9 @@ def test_attention_kernels_vs_numpy(dtype, n, d, kind):
     out.backward(d_out.to(DEV))
     pl = planes.detach().double().cpu().numpy()
     o_np, _, _, _ = A.attention_forward(pl[0], pl[1], pl[2], scale, bias_np)
-    gr = A.attention_backward(d_out.double().numpy(), pl[0], pl[1], pl[2], scale, bias_np)
+    # the backward re-reads the STORED output (bf16-rounded in bf16 mode) for delta = rowsum(dO*O)
+    gr = A.attention_backward(d_out.double().numpy(), pl[0], pl[1], pl[2], scale, bias_np,
+                              out=out.detach().double().cpu().numpy())
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     e = err_scaled if dtype == torch.float32 else err_rel
     assert e(out.float(), o_np) <= tol
