@@ -3,6 +3,12 @@
 # Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
+# tensor-core kernels first, each under a timeout: a broken one is reported and the run continues on SIMT
+for probe in attn qkv; do
+  timeout 300 python scripts/tc_probe.py $probe > gpurun_out/probe_$probe.log 2>&1
+  rc=$?; echo "probe $probe exit: $rc" >> gpurun_out/probe_$probe.log
+  if [ $rc -ne 0 ]; then export VRR_IMPL=simt; echo "PROBE $probe FAILED -> VRR_IMPL=simt"; tail -5 gpurun_out/probe_$probe.log; fi
+done
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 --timeout=300 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit: $?" >> gpurun_out/smoke.log

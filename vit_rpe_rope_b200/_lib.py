@@ -68,6 +68,10 @@ def load():
     if lib.vrr_abi_version() != 1:
         raise ImportError(f"libvrr_b200.so ABI {lib.vrr_abi_version()} != 1: rebuild")
     _lib = lib
+    # Debug switch (never set by the product): force one kernel family for the bf16 kernels.
+    forced = os.environ.get("VRR_IMPL", "").lower()
+    if forced in ("simt", "tcgen05"):
+        lib.vrr_set_impl(IMPL_SIMT if forced == "simt" else IMPL_TCGEN05)
     return lib
 
 

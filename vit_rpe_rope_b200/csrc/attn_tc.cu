@@ -317,8 +317,8 @@ EncodeTiledFn g_encode = nullptr;
 
 }  // namespace
 
-int make_tmap_bf16_rows64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t row_stride_bytes,
-                          uint32_t box_rows) {
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                   uint32_t box_rows) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -326,7 +326,7 @@ int make_tmap_bf16_rows64(CUtensorMap* map, const void* base, uint64_t rows, uin
     VRR_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, VRR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cuuint64_t dims[2] = {64, rows};
+  cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
@@ -350,7 +350,7 @@ int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float*
   VRR_REQUIRE(((uintptr_t)planes & 15) == 0 && ((uintptr_t)out & 15) == 0, VRR_ERR_INVALID_ARG,
               "attn_fwd (tcgen05): planes/out must be 16-byte aligned");
   CUtensorMap tmap;
-  if (int rc = make_tmap_bf16_rows64(&tmap, planes, (uint64_t)3 * B * H * N, kDh * 2, kKT)) return rc;
+  if (int rc = make_tmap_bf16(&tmap, planes, (uint64_t)3 * B * H * N, kDh, kDh * 2, kKT)) return rc;
   FwdParams p;
   p.out = (__nv_bfloat16*)out;
   p.lse = lse;

@@ -173,8 +173,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 }  // namespace tc
 
-// Host: build a 2-D bf16 tensor map (rows x 64 columns, 128-byte swizzle) over a dense buffer.
-int make_tmap_bf16_rows64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t row_stride_bytes,
-                          uint32_t box_rows);
+// Host: build a 2-D bf16 tensor map over a row-major [rows][cols] buffer with a box of
+// [box_rows][64 columns] (= 128 bytes wide) and 128-byte swizzle.
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                   uint32_t box_rows);
 
 }  // namespace vrr
