@@ -18,6 +18,12 @@ bool attn_fwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bia
 int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
                 int Dh, float scale, cudaStream_t st);
 
+// attn_bwd_tc.cu (tcgen05 / TMEM, bf16, Dh == 64)
+bool attn_bwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
+int attn_bwd_tc(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out, const float* lse,
+                void* d_planes, float* d_bias_param, float* delta, int B, int H, int N, int Dh, float scale,
+                cudaStream_t st);
+
 // gemm_simt.cu
 int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
                       int B, int N, int E, int H, int rope_mode, int dtype, cudaStream_t st);

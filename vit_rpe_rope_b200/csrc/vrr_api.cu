@@ -210,6 +210,12 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
   float* delta = (float*)workspace;
   size_t delta_bytes = (((size_t)B * H * N * sizeof(float) + 255) / 256) * 256;
   float* d_lut = (float*)((char*)workspace + delta_bytes);
+  const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_bwd_tc_supported(B, H, N, Dh, bias))
+    return attn_bwd_tc(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
+                       (cudaStream_t)stream);
+  VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
+              "attn_bwd: tcgen05 kernel forced but shape/dtype unsupported (bf16, Dh=64, poly degree <= 3)");
   return attn_bwd_simt(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, d_lut, B, H, N, Dh, scale,
                        dtype, (cudaStream_t)stream);
 }
