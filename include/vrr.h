@@ -88,21 +88,31 @@ uint64_t vrr_launch_count(void);
 /* ---- (c) patch embedding: models/vit.py:164,248-258 ---------------------------------------- */
 /* tokens[b][0][:]   = cls_token
  * tokens[b][1+p][:] = round_dtype(conv_weight[E][C*P*P] . unfold(images)[b][p][:] + conv_bias) (+ pos_embed[p])
- * images [B][C][Hi][Wi], weight [E][C][P][P], bias [E]            : element type `dtype`
+ * images [B][C][Hi][Wi]                                            : element type `img_dtype`
+ * weight [E][C][P][P], bias [E]                                    : element type `dtype` (the conv arithmetic)
  * cls_token [E], pos_embed, tokens [B][Np+1][E]                    : element type `tok_dtype`
  * pos_embed: NULL, or the absolute table [>= Np][E] (positional_encoding.py:37-40: added to patch
- * rows only).  (dtype, tok_dtype) = (bf16, fp32) is the reference's autocast semantics: the conv
- * result is bf16, the concatenation with the fp32 cls token promotes the stream to fp32. */
+ * rows only).  (img fp32, dtype bf16, tok fp32) is the reference's autocast semantics: the image is
+ * rounded to bf16 on load, the conv result is bf16, and the concatenation with the fp32 cls token
+ * promotes the stream to fp32.  The bf16 tensor-core path (P % 8 == 0, C*P*P % 64 == 0, E % 64 == 0)
+ * unfolds the patches into `workspace` (vrr_patch_embed_workspace_bytes, 256-byte aligned) and runs
+ * a tcgen05 GEMM; otherwise workspace may be NULL. */
+size_t vrr_patch_embed_workspace_bytes(int B, int C, int Hi, int Wi, int P, int E, int dtype);
 int vrr_patch_embed_fwd(const void* images, const void* weight, const void* bias,
-                        const void* cls_token, const void* pos_embed, void* tokens,
-                        int B, int C, int Hi, int Wi, int P, int E, int dtype, int tok_dtype,
-                        void* stream);
+                        const void* cls_token, const void* pos_embed, void* tokens, void* workspace,
+                        size_t workspace_bytes, int B, int C, int Hi, int Wi, int P, int E,
+                        int img_dtype, int dtype, int tok_dtype, void* stream);
+/* out[b*Np + p][c*P*P + i*P + j] = bf16(images[b][c][py*P+i][px*P+j]): the im2col matrix of the
+ * stride-P convolution (needs P % 8 == 0).  Used by the forward above and by callers that take the
+ * weight gradient with a plain library GEMM. */
+int vrr_patch_unfold(const void* images, void* out, int B, int C, int Hi, int Wi, int P,
+                     int img_dtype, void* stream);
 /* d_tokens [B][Np+1][E] (`tok_dtype`).  Parameter gradients are reductions and ALWAYS fp32:
- * d_weight [E][C*P*P], d_bias [E], d_cls [E], d_pos [Np][E] or NULL; written (not accumulated).
- * Images need no gradient (train.py:109-115). */
+ * d_weight [E][C*P*P] (or NULL: skip it), d_bias [E], d_cls [E], d_pos [Np][E] or NULL; written (not
+ * accumulated).  Images need no gradient (train.py:109-115). */
 int vrr_patch_embed_bwd(const void* images, const void* d_tokens, void* d_weight, void* d_bias,
                         void* d_cls, void* d_pos, int B, int C, int Hi, int Wi, int P, int E,
-                        int dtype, int tok_dtype, void* stream);
+                        int img_dtype, int dtype, int tok_dtype, void* stream);
 
 /* ---- (a) QKV projection with RoPE epilogue: models/vit.py:47-68, rope_utils.py:3-37 -------- */
 /* planes = split_heads(x . w_qkv^T) with q,k rows 1.. rotated by (cos,sin) in the epilogue.

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
 # tensor-core kernels first, each under a timeout: a broken one is reported and the run continues on SIMT
-for probe in attn qkv bwd; do
+for probe in attn qkv bwd patch; do
   timeout 300 python scripts/tc_probe.py $probe > gpurun_out/probe_$probe.log 2>&1
   rc=$?; echo "probe $probe exit: $rc" >> gpurun_out/probe_$probe.log
   if [ $rc -ne 0 ]; then export VRR_IMPL=simt; echo "PROBE $probe FAILED -> VRR_IMPL=simt"; tail -5 gpurun_out/probe_$probe.log; fi

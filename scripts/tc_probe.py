@@ -70,6 +70,28 @@ elif which == "qkv":
         ok = er < 2e-2 and bool(torch.isfinite(outs["tc"].float()).all())
         bad += (not ok)
         print(f"qkv_rope_fwd B={b} N={n} E={e_} H={h} rope={rope}: rel err tc vs simt {er:.3e} {'ok' if ok else 'BAD'}", flush=True)
+elif which == "patch":
+    for (b, c, hw, pch, e_, absolute, tdt) in [(4, 3, 224, 16, 768, False, torch.float32), (4, 3, 224, 16, 768, True, torch.float32),
+                                              (3, 3, 64, 8, 256, True, torch.float32), (2, 3, 64, 16, 128, True, torch.bfloat16),
+                                              (2, 1, 64, 8, 64, False, torch.float32), (5, 3, 384, 16, 1024, False, torch.float32)]:
+        gen = torch.Generator().manual_seed(hw + e_)
+        idt = torch.float32 if tdt == torch.float32 else torch.bfloat16
+        img = torch.randn(b, c, hw, hw, generator=gen).to(idt).to(dev)
+        w = (torch.randn(e_, c, pch, pch, generator=gen) * 0.05).to(torch.bfloat16).to(dev)
+        bias = (torch.randn(e_, generator=gen) * 0.1).to(torch.bfloat16).to(dev)
+        cls = (torch.randn(1, 1, e_, generator=gen) * 0.1).to(tdt).to(dev)
+        pos = (torch.randn(1, 700, e_, generator=gen) * 0.1).to(tdt).to(dev) if absolute else None
+        outs = {}
+        for name, impl in (("simt", _lib.IMPL_SIMT), ("tc", _lib.IMPL_TCGEN05)):
+            _lib.set_impl(impl)
+            o = ops.PatchEmbedFn.apply(img, w, bias, cls, pos, pch)
+            torch.cuda.synchronize()
+            outs[name] = o
+        er = rel(outs["tc"], outs["simt"])
+        ok = er < 1e-2 and bool(torch.isfinite(outs["tc"].float()).all())
+        bad += (not ok)
+        print(f"patch_embed B={b} C={c} img={hw} P={pch} E={e_} abs={absolute} tok={tdt}: rel err tc vs simt {er:.3e} "
+              f"{'ok' if ok else 'BAD'}", flush=True)
 elif which == "bwd":
     cases = [(2, 3, n, kind) for n in (197, 65, 1, 17, 64, 128, 129, 257, 577, 1025) for kind in ("none", "table", "poly", "polyh")]
     cases += [(32, 12, 197, "none"), (32, 12, 197, "table"), (32, 12, 197, "poly")]

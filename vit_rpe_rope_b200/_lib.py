@@ -36,8 +36,10 @@ SIGNATURES = {
     "vrr_device_ok": (c_int, []),
     "vrr_set_impl": (c_int, [c_int]),
     "vrr_launch_count": (c_uint64, []),
-    "vrr_patch_embed_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
-    "vrr_patch_embed_bwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
+    "vrr_patch_embed_workspace_bytes": (c_size_t, [c_int] * 7),
+    "vrr_patch_embed_fwd": (c_int, [c_void_p] * 7 + [c_size_t] + [c_int] * 9 + [c_void_p]),
+    "vrr_patch_unfold": (c_int, [c_void_p] * 2 + [c_int] * 6 + [c_void_p]),
+    "vrr_patch_embed_bwd": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "vrr_qkv_rope_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "vrr_qkv_rope_bwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
     "vrr_rope_apply": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),

@@ -27,14 +27,17 @@ struct StridedOperand {
 };
 
 // A[m][k] of unfold(images): m = b*Np + p (p = py*gw + px), k = c*P*P + i*P + j
-template <typename T>
+// TI = storage type of the images; ROUND = round each pixel to bf16 first (bf16 arithmetic on fp32
+// images, i.e. the reference's autocast cast of the conv input fused into the load).
+template <typename TI, bool ROUND>
 struct Im2colOperand {
-  const T* img;
+  const TI* img;
   int C, Hi, Wi, P, gw, Np;
   __device__ __forceinline__ float operator()(int m, int k) const {
     int b = m / Np, p = m - b * Np, py = p / gw, px = p - py * gw;
     int c = k / (P * P), r = k - c * P * P, i = r / P, j = r - i * P;
-    return Elem<T>::ld(img + (((long long)b * C + c) * Hi + (py * P + i)) * Wi + (px * P + j));
+    float v = Elem<TI>::ld(img + (((long long)b * C + c) * Hi + (py * P + i)) * Wi + (px * P + j));
+    return ROUND ? __bfloat162float(__float2bfloat16_rn(v)) : v;
   }
 };
 
@@ -237,6 +240,7 @@ int gemm_simt(const void* a, const void* b, void* c, int M, int N, int K, int ta
 }
 
 // ---- patch embedding --------------------------------------------------------------------------
+int patch_cls_rows(void* tokens, const void* cls, int B, int Np, int E, int tok_dtype, cudaStream_t st);
 template <typename T>
 __global__ void cls_rows_kernel(T* tokens, const T* cls, int B, int Np, int E) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,30 +249,40 @@ __global__ void cls_rows_kernel(T* tokens, const T* cls, int B, int Np, int E) {
   tokens[(size_t)b * (Np + 1) * E + e] = cls[e];
 }
 
-template <typename T, typename TT>
+template <typename TI, typename T, typename TT>
 static int patch_fwd_t(const void* images, const void* weight, const void* bias, const void* cls,
                        const void* pos, void* tokens, int B, int C, int Hi, int Wi, int P, int E,
                        cudaStream_t st) {
+  constexpr bool kRound = sizeof(TI) == 4 && sizeof(T) == 2;
+  using AOp = Im2colOperand<TI, kRound>;
   const int gh = Hi / P, gw = Wi / P, Np = gh * gw, Kd = C * P * P;
-  Im2colOperand<T> A{(const T*)images, C, Hi, Wi, P, gw, Np};
+  AOp A{(const TI*)images, C, Hi, Wi, P, gw, Np};
   StridedOperand<T> W{(const T*)weight, Kd, 1};
   PatchEmbedEpilogue<T, TT> epi{(TT*)tokens, (const T*)bias, (const TT*)pos, Np, E};
-  int rc = launch_gemm<Im2colOperand<T>, StridedOperand<T>, PatchEmbedEpilogue<T, TT>, true, true>(
+  int rc = launch_gemm<AOp, StridedOperand<T>, PatchEmbedEpilogue<T, TT>, true, true>(
       A, W, epi, B * Np, E, Kd, 1, st);
   if (rc) return rc;
-  cls_rows_kernel<TT><<<ceil_div(B * E, 256), 256, 0, st>>>((TT*)tokens, (const TT*)cls, B, Np, E);
+  return patch_cls_rows(tokens, cls, B, Np, E, sizeof(TT) == 4 ? VRR_F32 : VRR_BF16, st);
+}
+int patch_cls_rows(void* tokens, const void* cls, int B, int Np, int E, int tok_dtype, cudaStream_t st) {
+  if (tok_dtype == VRR_F32)
+    cls_rows_kernel<float><<<ceil_div(B * E, 256), 256, 0, st>>>((float*)tokens, (const float*)cls, B, Np, E);
+  else
+    cls_rows_kernel<__nv_bfloat16><<<ceil_div(B * E, 256), 256, 0, st>>>((__nv_bfloat16*)tokens, (const __nv_bfloat16*)cls, B, Np, E);
   VRR_LAUNCHED();
   return VRR_OK;
 }
 int patch_embed_fwd_simt(const void* images, const void* weight, const void* bias, const void* cls,
                          const void* pos, void* tokens, int B, int C, int Hi, int Wi, int P, int E,
-                         int dtype, int tok_dtype, cudaStream_t st) {
+                         int img_dtype, int dtype, int tok_dtype, cudaStream_t st) {
 #define ARGS images, weight, bias, cls, pos, tokens, B, C, Hi, Wi, P, E, st
-  if (dtype == VRR_F32 && tok_dtype == VRR_F32) return patch_fwd_t<float, float>(ARGS);
-  if (dtype == VRR_BF16 && tok_dtype == VRR_F32) return patch_fwd_t<__nv_bfloat16, float>(ARGS);
-  if (dtype == VRR_BF16 && tok_dtype == VRR_BF16) return patch_fwd_t<__nv_bfloat16, __nv_bfloat16>(ARGS);
+  if (img_dtype == VRR_F32 && dtype == VRR_F32 && tok_dtype == VRR_F32) return patch_fwd_t<float, float, float>(ARGS);
+  if (img_dtype == VRR_F32 && dtype == VRR_BF16 && tok_dtype == VRR_F32) return patch_fwd_t<float, __nv_bfloat16, float>(ARGS);
+  if (img_dtype == VRR_BF16 && dtype == VRR_BF16 && tok_dtype == VRR_F32) return patch_fwd_t<__nv_bfloat16, __nv_bfloat16, float>(ARGS);
+  if (img_dtype == VRR_BF16 && dtype == VRR_BF16 && tok_dtype == VRR_BF16)
+    return patch_fwd_t<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(ARGS);
 #undef ARGS
-  set_error("patch_embed_fwd: unsupported dtype combination (%d, tokens %d)", dtype, tok_dtype);
+  set_error("patch_embed_fwd: unsupported dtype combination (images %d, weights %d, tokens %d)", img_dtype, dtype, tok_dtype);
   return VRR_ERR_UNSUPPORTED;
 }
 
@@ -289,7 +303,7 @@ __global__ void token_batch_sum_kernel(const T* __restrict__ dtok, float* d_bias
   }
 }
 
-template <typename T, typename TT>
+template <typename TI, bool ROUND, typename TT>
 static int patch_bwd_t(const void* images, const void* d_tokens, float* d_weight, float* d_bias,
                        float* d_cls, float* d_pos, int B, int C, int Hi, int Wi, int P, int E,
                        cudaStream_t st) {
@@ -297,24 +311,28 @@ static int patch_bwd_t(const void* images, const void* d_tokens, float* d_weight
   VRR_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)E * sizeof(float), st));
   token_batch_sum_kernel<TT><<<ceil_div((Np + 1) * E, 256), 256, 0, st>>>((const TT*)d_tokens, d_bias, d_cls, d_pos, B, Np, E);
   VRR_LAUNCHED();
+  if (!d_weight) return VRR_OK;  // caller computes the weight gradient itself (plain library GEMM)
   // d_weight[e][k] = sum_m d_tokens[m][e] * unfold(images)[m][k]   (reduction over m = tokens)
+  using BOp = SwapArgs<Im2colOperand<TI, ROUND>>;
   PatchGradOperand<TT> A{(const TT*)d_tokens, Np, E};
-  SwapArgs<Im2colOperand<T>> Bo{Im2colOperand<T>{(const T*)images, C, Hi, Wi, P, gw, Np}};
+  BOp Bo{Im2colOperand<TI, ROUND>{(const TI*)images, C, Hi, Wi, P, gw, Np}};
   const int tiles = ceil_div(E, BM) * ceil_div(Kd, BN);
   int splits = max(1, min(ceil_div(2 * sm_count(), tiles), Mtok / (4 * BK)));
   VRR_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)E * Kd * sizeof(float), st));
-  return launch_gemm<PatchGradOperand<TT>, SwapArgs<Im2colOperand<T>>, AtomicEpilogue, false, false>(
+  return launch_gemm<PatchGradOperand<TT>, BOp, AtomicEpilogue, false, false>(
       A, Bo, AtomicEpilogue{d_weight, Kd}, E, Kd, Mtok, splits, st);
 }
 int patch_embed_bwd_simt(const void* images, const void* d_tokens, float* d_weight, float* d_bias,
                          float* d_cls, float* d_pos, int B, int C, int Hi, int Wi, int P, int E,
-                         int dtype, int tok_dtype, cudaStream_t st) {
+                         int img_dtype, int dtype, int tok_dtype, cudaStream_t st) {
 #define ARGS images, d_tokens, d_weight, d_bias, d_cls, d_pos, B, C, Hi, Wi, P, E, st
-  if (dtype == VRR_F32 && tok_dtype == VRR_F32) return patch_bwd_t<float, float>(ARGS);
-  if (dtype == VRR_BF16 && tok_dtype == VRR_F32) return patch_bwd_t<__nv_bfloat16, float>(ARGS);
-  if (dtype == VRR_BF16 && tok_dtype == VRR_BF16) return patch_bwd_t<__nv_bfloat16, __nv_bfloat16>(ARGS);
+  if (img_dtype == VRR_F32 && dtype == VRR_F32 && tok_dtype == VRR_F32) return patch_bwd_t<float, false, float>(ARGS);
+  if (img_dtype == VRR_F32 && dtype == VRR_BF16 && tok_dtype == VRR_F32) return patch_bwd_t<float, true, float>(ARGS);
+  if (img_dtype == VRR_BF16 && dtype == VRR_BF16 && tok_dtype == VRR_F32) return patch_bwd_t<__nv_bfloat16, false, float>(ARGS);
+  if (img_dtype == VRR_BF16 && dtype == VRR_BF16 && tok_dtype == VRR_BF16)
+    return patch_bwd_t<__nv_bfloat16, false, __nv_bfloat16>(ARGS);
 #undef ARGS
-  set_error("patch_embed_bwd: unsupported dtype combination (%d, tokens %d)", dtype, tok_dtype);
+  set_error("patch_embed_bwd: unsupported dtype combination (images %d, weights %d, tokens %d)", img_dtype, dtype, tok_dtype);
   return VRR_ERR_UNSUPPORTED;
 }
 

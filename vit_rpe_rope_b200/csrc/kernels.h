@@ -30,16 +30,24 @@ int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const 
 int gemm_simt(const void* a, const void* b, void* c, int M, int N, int K, int ta, int tb, int dtype,
               int c_dtype, cudaStream_t st);
 int patch_embed_fwd_simt(const void* images, const void* weight, const void* bias, const void* cls,
-                         const void* pos, void* tokens, int B, int C, int Hi, int Wi, int P, int E, int dtype,
-                         int tok_dtype, cudaStream_t st);
+                         const void* pos, void* tokens, int B, int C, int Hi, int Wi, int P, int E, int img_dtype,
+                         int dtype, int tok_dtype, cudaStream_t st);
 int patch_embed_bwd_simt(const void* images, const void* d_tokens, float* d_weight, float* d_bias, float* d_cls,
-                         float* d_pos, int B, int C, int Hi, int Wi, int P, int E, int dtype, int tok_dtype,
-                         cudaStream_t st);
+                         float* d_pos, int B, int C, int Hi, int Wi, int P, int E, int img_dtype, int dtype,
+                         int tok_dtype, cudaStream_t st);
+int patch_cls_rows(void* tokens, const void* cls, int B, int Np, int E, int tok_dtype, cudaStream_t st);
 
 // gemm_tc.cu (tcgen05 / TMEM / TMA, bf16)
 bool qkv_rope_fwd_tc_supported(int B, int N, int E, int H);
 int qkv_rope_fwd_tc(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
                     int B, int N, int E, int H, int rope_mode, cudaStream_t st);
+
+bool patch_embed_tc_supported(int B, int C, int Hi, int Wi, int P, int E);
+size_t patch_embed_tc_workspace_bytes(int B, int C, int Hi, int Wi, int P);
+int patch_unfold(const void* images, void* out, int B, int C, int Hi, int Wi, int P, int img_dtype, cudaStream_t st);
+int patch_embed_fwd_tc(const void* images, const void* weight, const void* bias, const void* pos, void* tokens,
+                       void* workspace, int B, int C, int Hi, int Wi, int P, int E, int img_dtype, int tok_dtype,
+                       cudaStream_t st);
 
 // rope.cu
 int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,

@@ -7,49 +7,102 @@
 
 namespace vrr {
 
-template <typename T>
+// One thread = VEC consecutive channels dd..dd+VEC-1 of the first half (and their partners dd+Dh/2..)
+// of one (head, token), looping over a chunk of the batch: 16-byte loads/stores throughout.
+template <typename T, int VEC>
+struct VecIO;
+template <>
+struct VecIO<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 x = *reinterpret_cast<const float4*>(p);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct VecIO<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 x = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+      v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 x;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    x.x = *reinterpret_cast<uint32_t*>(&a); x.y = *reinterpret_cast<uint32_t*>(&b);
+    x.z = *reinterpret_cast<uint32_t*>(&c); x.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = x;
+  }
+};
+
+template <typename T, int VEC>
 __global__ void qkv_rope_bwd_kernel(const T* __restrict__ d_planes, const T* __restrict__ planes,
                                     const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                                     T* __restrict__ d_qkv, float* d_cos, float* d_sin, int B, int N,
                                     int E, int H, int Dh, int rope_mode, int b_chunk) {
-  const int hd = Dh >> 1;
+  const int hd = Dh >> 1, nv = hd / VEC;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= H * N * hd) return;
-  const int dd = idx % hd, t = (idx / hd) % N, h = idx / (hd * N);
+  if (idx >= H * N * nv) return;
+  const int dd = (idx % nv) * VEC, t = (idx / nv) % N, h = idx / (nv * N);
   const int b0 = blockIdx.y * b_chunk, b1 = min(B, b0 + b_chunk);
   const size_t plane = (size_t)B * H * N * Dh;
   const bool rot = rope_mode != VRR_ROPE_NONE && t >= 1;
-  float c = 1.f, s = 0.f;
+  float c[VEC], s[VEC], acc_c[VEC], acc_s[VEC];
   size_t tab = 0;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { c[e] = 1.f; s[e] = 0.f; acc_c[e] = 0.f; acc_s[e] = 0.f; }
   if (rot) {
     tab = ((size_t)(rope_mode == VRR_ROPE_MIXED ? h * (N - 1) : 0) + (t - 1)) * hd + dd;
-    c = cos_tab[tab];
-    s = sin_tab[tab];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { c[e] = cos_tab[tab + e]; s[e] = sin_tab[tab + e]; }
   }
-  float acc_c = 0.f, acc_s = 0.f;
+  const bool want_cs = rot && d_cos != nullptr;
   for (int b = b0; b < b1; ++b) {
     const size_t src = (((size_t)b * H + h) * N + t) * Dh + dd;
     T* dst = d_qkv + ((size_t)b * N + t) * (3 * E) + h * Dh + dd;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      const float g1 = Elem<T>::ld(d_planes + which * plane + src);
-      const float g2 = Elem<T>::ld(d_planes + which * plane + src + hd);
-      Elem<T>::st(dst + which * E, g1 * c + g2 * s);
-      Elem<T>::st(dst + which * E + hd, g2 * c - g1 * s);
-      if (rot && d_cos) {
-        const float r1 = Elem<T>::ld(planes + which * plane + src);
-        const float r2 = Elem<T>::ld(planes + which * plane + src + hd);
-        const float x1 = r1 * c + r2 * s, x2 = r2 * c - r1 * s;  // un-rotated activations
-        acc_c += g1 * x1 + g2 * x2;
-        acc_s += g2 * x1 - g1 * x2;
+      float g1[VEC], g2[VEC], o1[VEC], o2[VEC];
+      VecIO<T, VEC>::ld(d_planes + which * plane + src, g1);
+      VecIO<T, VEC>::ld(d_planes + which * plane + src + hd, g2);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        o1[e] = g1[e] * c[e] + g2[e] * s[e];
+        o2[e] = g2[e] * c[e] - g1[e] * s[e];
+      }
+      VecIO<T, VEC>::st(dst + which * E, o1);
+      VecIO<T, VEC>::st(dst + which * E + hd, o2);
+      if (want_cs) {
+        float r1[VEC], r2[VEC];
+        VecIO<T, VEC>::ld(planes + which * plane + src, r1);
+        VecIO<T, VEC>::ld(planes + which * plane + src + hd, r2);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float x1 = r1[e] * c[e] + r2[e] * s[e], x2 = r2[e] * c[e] - r1[e] * s[e];  // un-rotated
+          acc_c[e] += g1[e] * x1 + g2[e] * x2;
+          acc_s[e] += g2[e] * x1 - g1[e] * x2;
+        }
       }
     }
-    dst[2 * E] = d_planes[2 * plane + src];
-    dst[2 * E + hd] = d_planes[2 * plane + src + hd];
+    float v1[VEC], v2[VEC];
+    VecIO<T, VEC>::ld(d_planes + 2 * plane + src, v1);
+    VecIO<T, VEC>::ld(d_planes + 2 * plane + src + hd, v2);
+    VecIO<T, VEC>::st(dst + 2 * E, v1);
+    VecIO<T, VEC>::st(dst + 2 * E + hd, v2);
   }
-  if (rot && d_cos) {
-    atomicAdd(d_cos + tab, acc_c);
-    atomicAdd(d_sin + tab, acc_s);
+  if (want_cs) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      atomicAdd(d_cos + tab + e, acc_c[e]);
+      atomicAdd(d_sin + tab + e, acc_s[e]);
+    }
   }
 }
 
@@ -63,17 +116,21 @@ int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab,
     VRR_CUDA(cudaMemsetAsync(d_cos, 0, n, st));
     VRR_CUDA(cudaMemsetAsync(d_sin, 0, n, st));
   }
-  const int threads = 128, blocks = ceil_div(H * N * hd, threads);
+  const int vec = dtype == VRR_F32 ? 4 : 8;
+  VRR_REQUIRE(hd % vec == 0, VRR_ERR_UNSUPPORTED, "qkv_rope_bwd: head dim %d too small for %d-wide access", Dh, vec);
+  VRR_REQUIRE(((uintptr_t)d_planes & 15) == 0 && ((uintptr_t)planes & 15) == 0 && ((uintptr_t)d_qkv & 15) == 0,
+              VRR_ERR_INVALID_ARG, "qkv_rope_bwd: pointers must be 16-byte aligned");
+  const int threads = 128, blocks = ceil_div(H * N * (hd / vec), threads);
   int chunks = 1;
-  while (chunks < B && blocks * chunks < 4 * sm_count()) chunks *= 2;
+  while (chunks < B && blocks * chunks < 8 * sm_count()) chunks *= 2;
   const int b_chunk = ceil_div(B, chunks);
   dim3 grid(blocks, ceil_div(B, b_chunk));
   if (dtype == VRR_F32)
-    qkv_rope_bwd_kernel<float><<<grid, threads, 0, st>>>((const float*)d_planes, (const float*)planes, cos_tab,
-                                                        sin_tab, (float*)d_qkv, d_cos, d_sin, B, N, E, H, Dh,
-                                                        rope_mode, b_chunk);
+    qkv_rope_bwd_kernel<float, 4><<<grid, threads, 0, st>>>((const float*)d_planes, (const float*)planes, cos_tab,
+                                                           sin_tab, (float*)d_qkv, d_cos, d_sin, B, N, E, H, Dh,
+                                                           rope_mode, b_chunk);
   else
-    qkv_rope_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(
+    qkv_rope_bwd_kernel<__nv_bfloat16, 8><<<grid, threads, 0, st>>>(
         (const __nv_bfloat16*)d_planes, (const __nv_bfloat16*)planes, cos_tab, sin_tab,
         (__nv_bfloat16*)d_qkv, d_cos, d_sin, B, N, E, H, Dh, rope_mode, b_chunk);
   VRR_LAUNCHED();

@@ -87,28 +87,54 @@ int vrr_set_impl(int impl) {
 }
 uint64_t vrr_launch_count(void) { return g_launches.load(); }
 
+size_t vrr_patch_embed_workspace_bytes(int B, int C, int Hi, int Wi, int P, int E, int dtype) {
+  if (dtype != VRR_BF16 || P <= 0 || !patch_embed_tc_supported(B, C, Hi, Wi, P, E)) return 0;
+  return patch_embed_tc_workspace_bytes(B, C, Hi, Wi, P);
+}
+
 int vrr_patch_embed_fwd(const void* images, const void* weight, const void* bias, const void* cls_token,
-                        const void* pos_embed, void* tokens, int B, int C, int Hi, int Wi, int P, int E,
-                        int dtype, int tok_dtype, void* stream) {
+                        const void* pos_embed, void* tokens, void* workspace, size_t workspace_bytes, int B, int C,
+                        int Hi, int Wi, int P, int E, int img_dtype, int dtype, int tok_dtype, void* stream) {
   VRR_REQUIRE(images && weight && bias && cls_token && tokens, VRR_ERR_INVALID_ARG, "patch_embed_fwd: NULL pointer");
-  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(tok_dtype), VRR_ERR_INVALID_ARG, "patch_embed_fwd: bad dtype %d/%d", dtype, tok_dtype);
+  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(tok_dtype) && dtype_ok(img_dtype), VRR_ERR_INVALID_ARG,
+              "patch_embed_fwd: bad dtype %d/%d/%d", img_dtype, dtype, tok_dtype);
   VRR_REQUIRE(B > 0 && C > 0 && P > 0 && E > 0 && Hi >= P && Wi >= P, VRR_ERR_INVALID_ARG,
               "patch_embed_fwd: bad sizes B=%d C=%d Hi=%d Wi=%d P=%d E=%d", B, C, Hi, Wi, P, E);
   if (int rc = require_device()) return rc;
-  return patch_embed_fwd_simt(images, weight, bias, cls_token, pos_embed, tokens, B, C, Hi, Wi, P, E, dtype,
+  const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && patch_embed_tc_supported(B, C, Hi, Wi, P, E)) {
+    const size_t need = patch_embed_tc_workspace_bytes(B, C, Hi, Wi, P);
+    VRR_REQUIRE(workspace && workspace_bytes >= need, VRR_ERR_WORKSPACE,
+                "patch_embed_fwd: workspace %zu < %zu bytes (vrr_patch_embed_workspace_bytes)", workspace_bytes, need);
+    VRR_REQUIRE(((uintptr_t)workspace & 255) == 0, VRR_ERR_INVALID_ARG, "patch_embed_fwd: workspace must be 256-byte aligned");
+    if (int rc = patch_embed_fwd_tc(images, weight, bias, pos_embed, tokens, workspace, B, C, Hi, Wi, P, E, img_dtype,
+                                    tok_dtype, (cudaStream_t)stream))
+      return rc;
+    return patch_cls_rows(tokens, cls_token, B, (Hi / P) * (Wi / P), E, tok_dtype, (cudaStream_t)stream);
+  }
+  return patch_embed_fwd_simt(images, weight, bias, cls_token, pos_embed, tokens, B, C, Hi, Wi, P, E, img_dtype, dtype,
                               tok_dtype, (cudaStream_t)stream);
 }
 
+int vrr_patch_unfold(const void* images, void* out, int B, int C, int Hi, int Wi, int P, int img_dtype, void* stream) {
+  VRR_REQUIRE(images && out, VRR_ERR_INVALID_ARG, "patch_unfold: NULL pointer");
+  VRR_REQUIRE(dtype_ok(img_dtype), VRR_ERR_INVALID_ARG, "patch_unfold: bad dtype %d", img_dtype);
+  VRR_REQUIRE(B > 0 && C > 0 && P > 0 && Hi >= P && Wi >= P, VRR_ERR_INVALID_ARG, "patch_unfold: bad sizes");
+  if (int rc = require_device()) return rc;
+  return patch_unfold(images, out, B, C, Hi, Wi, P, img_dtype, (cudaStream_t)stream);
+}
+
 int vrr_patch_embed_bwd(const void* images, const void* d_tokens, void* d_weight, void* d_bias, void* d_cls,
-                        void* d_pos, int B, int C, int Hi, int Wi, int P, int E, int dtype, int tok_dtype,
-                        void* stream) {
-  VRR_REQUIRE(images && d_tokens && d_weight && d_bias && d_cls, VRR_ERR_INVALID_ARG, "patch_embed_bwd: NULL pointer");
-  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(tok_dtype), VRR_ERR_INVALID_ARG, "patch_embed_bwd: bad dtype %d/%d", dtype, tok_dtype);
+                        void* d_pos, int B, int C, int Hi, int Wi, int P, int E, int img_dtype, int dtype,
+                        int tok_dtype, void* stream) {
+  VRR_REQUIRE(images && d_tokens && d_bias && d_cls, VRR_ERR_INVALID_ARG, "patch_embed_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(tok_dtype) && dtype_ok(img_dtype), VRR_ERR_INVALID_ARG,
+              "patch_embed_bwd: bad dtype %d/%d/%d", img_dtype, dtype, tok_dtype);
   VRR_REQUIRE(B > 0 && C > 0 && P > 0 && E > 0 && Hi >= P && Wi >= P, VRR_ERR_INVALID_ARG,
               "patch_embed_bwd: bad sizes");
   if (int rc = require_device()) return rc;
   return patch_embed_bwd_simt(images, d_tokens, (float*)d_weight, (float*)d_bias, (float*)d_cls, (float*)d_pos, B,
-                              C, Hi, Wi, P, E, dtype, tok_dtype, (cudaStream_t)stream);
+                              C, Hi, Wi, P, E, img_dtype, dtype, tok_dtype, (cudaStream_t)stream);
 }
 
 int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, const float* sin_tab, void* planes,

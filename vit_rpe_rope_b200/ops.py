@@ -74,8 +74,9 @@ class _timed:
 class PatchEmbedFn(torch.autograd.Function):
     """tokens[B, Np+1, E] from images: unfold + GEMM + bias (+ absolute pos_embed) + cls row.
 
-    images / weight / bias share the conv dtype; cls_token / pos_embed / tokens share the token-stream
-    dtype (fp32 under autocast, like the reference's cat with the fp32 cls token)."""
+    weight / bias carry the conv dtype; cls_token / pos_embed / tokens the token-stream dtype (fp32
+    under autocast, like the reference's cat with the fp32 cls token); images may stay fp32 when the
+    conv runs in bf16 - the rounding is fused into the kernel's load."""
 
     @staticmethod
     def forward(ctx, images, weight, bias, cls_token, pos_embed, patch):
@@ -83,9 +84,11 @@ class PatchEmbedFn(torch.autograd.Function):
         lib = _lib.load()
         B, C, Hi, Wi = images.shape
         E = weight.shape[0]
-        dt, tdt = images.dtype, cls_token.dtype
-        if weight.dtype != dt or bias.dtype != dt or (pos_embed is not None and pos_embed.dtype != tdt):
-            raise TypeError("patch_embed: images/weight/bias must share a dtype, cls_token/pos_embed another")
+        idt, dt, tdt = images.dtype, weight.dtype, cls_token.dtype
+        if bias.dtype != dt or (pos_embed is not None and pos_embed.dtype != tdt):
+            raise TypeError("patch_embed: weight/bias must share a dtype, cls_token/pos_embed another")
+        if idt != dt and not (idt == torch.float32 and dt == torch.bfloat16):
+            raise TypeError(f"patch_embed: images {idt} with weights {dt} is not supported")
         images = images.contiguous()
         w = weight.detach().contiguous()
         b = bias.detach().contiguous()
@@ -97,30 +100,43 @@ class PatchEmbedFn(torch.autograd.Function):
                 raise RuntimeError(f"absolute pos_embed has {pos_embed.shape[-2]} rows, need {Np}")
             pos = pos_embed.detach().reshape(-1, E).contiguous()
         tokens = torch.empty(B, Np + 1, E, device=images.device, dtype=tdt)
-        with torch.cuda.device(images.device):
-            _lib.check(lib.vrr_patch_embed_fwd(_ptr(images), _ptr(w), _ptr(b), _ptr(cls), _ptr(pos),
-                                               _ptr(tokens), B, C, Hi, Wi, patch, E, _DT[dt], _DT[tdt],
-                                               _stream()), "vrr_patch_embed_fwd")
+        ws_bytes = int(lib.vrr_patch_embed_workspace_bytes(B, C, Hi, Wi, patch, E, _DT[dt]))
+        ws = torch.empty(ws_bytes, device=images.device, dtype=torch.uint8) if ws_bytes else None
+        with torch.cuda.device(images.device), _timed("patch_embed_fwd"):
+            _lib.check(lib.vrr_patch_embed_fwd(_ptr(images), _ptr(w), _ptr(b), _ptr(cls), _ptr(pos), _ptr(tokens),
+                                               _ptr(ws), ws_bytes, B, C, Hi, Wi, patch, E, _DT[idt], _DT[dt],
+                                               _DT[tdt], _stream()), "vrr_patch_embed_fwd")
         ctx.save_for_backward(images)
         ctx.meta = (B, C, Hi, Wi, patch, E, Np, pos_embed.shape if pos_embed is not None else None,
-                    weight.shape, cls_token.shape, dt, tdt)
+                    weight.shape, cls_token.shape, idt, dt, tdt)
         return tokens
 
     @staticmethod
     def backward(ctx, d_tokens):
         lib = _lib.load()
         (images,) = ctx.saved_tensors
-        B, C, Hi, Wi, patch, E, Np, pos_shape, w_shape, cls_shape, dt, tdt = ctx.meta
+        B, C, Hi, Wi, patch, E, Np, pos_shape, w_shape, cls_shape, idt, dt, tdt = ctx.meta
         d_tokens = d_tokens.contiguous()
         dev = images.device
-        d_w = torch.empty(E, C * patch * patch, device=dev, dtype=torch.float32)
+        K = C * patch * patch
+        # bf16: the weight gradient is a plain GEMM d_tokens^T . unfold(images) -> cuBLAS (allowed for
+        # library-shaped GEMMs); fp32: the library's FFMA split-K GEMM with the unfold fused in.
+        own_dw = not (dt == torch.bfloat16 and patch % 8 == 0 and Wi % 4 == 0)
+        d_w = torch.empty(E, K, device=dev, dtype=torch.float32) if own_dw else None
         d_b = torch.empty(E, device=dev, dtype=torch.float32)
         d_cls = torch.empty(E, device=dev, dtype=torch.float32)
         d_pos_rows = torch.empty(Np, E, device=dev, dtype=torch.float32) if pos_shape is not None else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed("patch_embed_bwd"):
             _lib.check(lib.vrr_patch_embed_bwd(_ptr(images), _ptr(d_tokens), _ptr(d_w), _ptr(d_b), _ptr(d_cls),
-                                               _ptr(d_pos_rows), B, C, Hi, Wi, patch, E, _DT[dt], _DT[tdt],
+                                               _ptr(d_pos_rows), B, C, Hi, Wi, patch, E, _DT[idt], _DT[dt], _DT[tdt],
                                                _stream()), "vrr_patch_embed_bwd")
+            if not own_dw:
+                unf = torch.empty(B * Np, K, device=dev, dtype=torch.bfloat16)
+                _lib.check(lib.vrr_patch_unfold(_ptr(images), _ptr(unf), B, C, Hi, Wi, patch, _DT[idt], _stream()),
+                           "vrr_patch_unfold")
+                g = d_tokens[:, 1:, :].reshape(B * Np, E).to(torch.bfloat16)
+                with torch.autocast("cuda", enabled=False):
+                    d_w = torch.matmul(g.t(), unf)
         d_pos = None
         if pos_shape is not None:
             d_pos = torch.zeros(pos_shape, device=dev, dtype=tdt)
@@ -129,11 +145,14 @@ class PatchEmbedFn(torch.autograd.Function):
 
 
 def patch_embed(images, weight, bias, cls_token, pos_embed, patch):
-    """Conv operands are cast to the compute dtype (autograd-tracked casts keep fp32 master grads);
-    under autocast the token stream (cls, pos, output) stays fp32 as in the reference."""
+    """Conv weights are cast to the compute dtype (autograd-tracked casts keep fp32 master grads);
+    under autocast the token stream (cls, pos, output) stays fp32 as in the reference, and fp32 images
+    are passed as they are (rounded to bf16 inside the kernel)."""
     dt = compute_dtype(images)
     tdt = torch.float32 if torch.is_autocast_enabled("cuda") else dt
-    return PatchEmbedFn.apply(images.to(dt), weight.to(dt), bias.to(dt), cls_token.to(tdt),
+    if not (images.dtype == torch.float32 and dt == torch.bfloat16):
+        images = images.to(dt)
+    return PatchEmbedFn.apply(images, weight.to(dt), bias.to(dt), cls_token.to(tdt),
                               None if pos_embed is None else pos_embed.to(tdt), patch)
 
 
