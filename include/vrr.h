@@ -84,6 +84,11 @@ int vrr_device_ok(void);                   /* 1 if the current device is sm_100,
 int vrr_set_impl(int impl);                /* vrr_impl; process-wide; returns previous value    */
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t vrr_launch_count(void);
+/* Tuning / experiment switches (process-wide).  "attn_fwd_key_tile" = 64 (default) or 128. */
+int vrr_set_option(const char* name, int value);
+/* Debug: one CTA of the next attention-forward launches records clock64() phase stamps (8 per key
+ * tile, first 8 tiles) into `device_buf` (64 x int64); NULL switches it off. */
+int vrr_debug_timestamps(void* device_buf);
 
 /* ---- (c) patch embedding: models/vit.py:164,248-258 ---------------------------------------- */
 /* tokens[b][0][:]   = cls_token

@@ -36,6 +36,8 @@ SIGNATURES = {
     "vrr_device_ok": (c_int, []),
     "vrr_set_impl": (c_int, [c_int]),
     "vrr_launch_count": (c_uint64, []),
+    "vrr_set_option": (c_int, [c_char_p, c_int]),
+    "vrr_debug_timestamps": (c_int, [c_void_p]),
     "vrr_patch_embed_workspace_bytes": (c_size_t, [c_int] * 7),
     "vrr_patch_embed_fwd": (c_int, [c_void_p] * 7 + [c_size_t] + [c_int] * 9 + [c_void_p]),
     "vrr_patch_unfold": (c_int, [c_void_p] * 2 + [c_int] * 6 + [c_void_p]),

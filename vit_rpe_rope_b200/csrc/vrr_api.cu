@@ -86,6 +86,20 @@ int vrr_set_impl(int impl) {
   return g_impl.exchange(impl);
 }
 uint64_t vrr_launch_count(void) { return g_launches.load(); }
+int vrr_debug_timestamps(void* device_buf) {  /* 64 x int64 device buffer, or NULL to switch off */
+  attn_fwd_tc_set_debug((long long*)device_buf);
+  return VRR_OK;
+}
+int vrr_set_option(const char* name, int value) {
+  if (!name) return VRR_ERR_INVALID_ARG;
+  if (!strcmp(name, "attn_fwd_key_tile")) { attn_fwd_tc_set_key_tile(value); return VRR_OK; }
+  if (!strcmp(name, "attn_fwd_variant")) { attn_fwd_tc_set_variant(value); return VRR_OK; }
+  if (!strcmp(name, "attn_fwd_smem_pad_kb")) { attn_fwd_tc_set_smem_pad_kb(value); return VRR_OK; }
+  if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
+  if (!strcmp(name, "attn_fwd_rescale_threshold_x100")) { attn_fwd_tc_set_threshold_x100(value); return VRR_OK; }
+  set_error("vrr_set_option: unknown option '%s'", name);
+  return VRR_ERR_INVALID_ARG;
+}
 
 size_t vrr_patch_embed_workspace_bytes(int B, int C, int Hi, int Wi, int P, int E, int dtype) {
   if (dtype != VRR_BF16 || P <= 0 || !patch_embed_tc_supported(B, C, Hi, Wi, P, E)) return 0;
