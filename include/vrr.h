@@ -164,6 +164,18 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
                  size_t workspace_bytes, int B, int H, int N, int Dh, float scale, int dtype,
                  void* stream);
 
+/* ---- (f) N1, first "next" row: LayerNorm of the token stream, models/vit.py:113,117,122,124,210 - */
+/* y = (x - mean) * rstd * gamma + beta over the last dimension (nn.LayerNorm, biased variance, eps
+ * inside the sqrt).  x [M][E] (`x_dtype`), y [M][E] (`y_dtype`: the consumer GEMM's dtype, so that
+ * under autocast the fp32 -> bf16 cast of the reference is fused into the store), gamma/beta fp32 [E],
+ * mean/rstd fp32 [M] (saved for the backward). */
+int vrr_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                      float* rstd, int M, int E, float eps, int x_dtype, int y_dtype, void* stream);
+/* dx [M][E] (`x_dtype`), dgamma/dbeta fp32 [E] (written, not accumulated), from dy [M][E] (`y_dtype`). */
+int vrr_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, float* dgamma, float* dbeta, int M, int E,
+                      int x_dtype, int y_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

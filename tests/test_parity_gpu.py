@@ -359,6 +359,34 @@ def test_patch_embed_kernel_vs_conv2d(dtype, b, c, hw, p, e, absolute):
             assert e_(got.grad.float(), want.grad) <= tol
 
 
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("m,e", [(1, 32), (7, 48), (130, 192), (515, 768), (64, 1024), (3, 100)])
+def test_layernorm_kernel_vs_torch(xdt, ydt, m, e):
+    """LayerNorm fwd/bwd (N1) vs float64 F.layer_norm: any width (vectorised when E % 128 == 0), the
+    autocast combination fp32 in / bf16 out, gamma / beta gradients reduced over all rows."""
+    g = torch.Generator().manual_seed(e + m)
+    x = (torch.randn(m, e, generator=g) * 1.7 + 0.3).to(xdt)
+    w = torch.randn(e, generator=g) * 0.5 + 1.0
+    b = torch.randn(e, generator=g) * 0.2
+    dy = torch.randn(m, e, generator=g).to(ydt)
+    xs = x.to(DEV).requires_grad_(True)
+    ws, bs = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    y = ops.LayerNormFn.apply(xs, ws, bs, 1e-5, ydt)
+    assert y.dtype == ydt
+    y.backward(dy.to(DEV))
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (e,), wr, br, 1e-5)
+    yr.backward(dy.double())
+    exact = xdt == torch.float32 and ydt == torch.float32
+    tol, err = (FP32_TOL, err_scaled) if exact else (BF16_TOL, err_rel)
+    assert err(y.float(), yr) <= tol
+    assert err(xs.grad.float(), xr.grad) <= tol
+    assert err(ws.grad, wr.grad) <= (tol if exact else 1e-3 + tol)
+    assert err(bs.grad, br.grad) <= tol
+
+
 @pytest.mark.parametrize("rope", ["axial", "mixed"])
 def test_apply_rotary_emb_public_function(rope):
     b, h, n, d = 2, 3, 16, 32

@@ -55,6 +55,12 @@ int patch_embed_fwd_tc(const void* images, const void* weight, const void* bias,
                        void* workspace, int B, int C, int Hi, int Wi, int P, int E, int img_dtype, int tok_dtype,
                        cudaStream_t st);
 
+// layernorm.cu
+int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int E,
+                  float eps, int x_dtype, int y_dtype, cudaStream_t st);
+int layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                  float* dgamma, float* dbeta, int M, int E, int x_dtype, int y_dtype, cudaStream_t st);
+
 // rope.cu
 int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,
                  void* d_qkv, float* d_cos, float* d_sin, int B, int N, int E, int H, int rope_mode, int dtype,

@@ -1,0 +1,233 @@
+// LayerNorm forward / backward for the token stream (row N1 of SURVEY.md section 8(f): the first
+// "next" component after the attention path).  Replaces nn.LayerNorm at models/vit.py:113,117,122,124,
+// 210 of the reference: y = (x - mean) * rstd * gamma + beta over the last dimension, eps 1e-5.
+//
+// Why a kernel of our own: under autocast the reference's LayerNorm runs in fp32 and every consumer
+// (qkv / fc1 GEMM) then casts its output to bf16 - two extra passes over [B*N, E]; and ATen's
+// gamma/beta-gradient kernel alone was 14 % of the ViT-B/16 training step (profiles/r1_summary.md).
+// Here the forward writes the consumer's dtype directly (same rounding point as the reference: fp32
+// math, one rounding to bf16) and the backward produces dx, dgamma, dbeta in ONE pass over dy and x.
+//
+// One warp per row, rows grid-strided over a persistent grid; the row (<= a few KB) is re-read from
+// L1 for the second pass instead of being held in registers, so any E works.  HBM-bound:
+//   fwd  : read x, write y                      (E*(sx + sy) bytes per row)
+//   bwd  : read dy, x, write dx                 (E*(sy + sx + sx) bytes per row)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vrr {
+
+namespace {
+
+constexpr int kLnWarps = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// VEC = 4: E % 128 == 0, 16-byte (fp32) / 8-byte (bf16) accesses; VEC = 1: any E.
+template <typename TX, typename TY, int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int E,
+              float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_e = 1.f / (float)E;
+  for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+    const TX* xr = x + (size_t)row * E;
+    TY* yr = y + (size_t)row * E;
+    float s = 0.f;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 v = ld4(xr + c);
+        s += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) s += Elem<TX>::ld(xr + c);
+    }
+    const float mean = warp_sum(s) * inv_e;
+    float q = 0.f;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 v = ld4(xr + c);
+        const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float a = Elem<TX>::ld(xr + c) - mean;
+        q += a * a;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_e + eps);
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 v = ld4(xr + c), g = ld4(gamma + c), b = ld4(beta + c);
+        float4 o;
+        o.x = (v.x - mean) * rstd * g.x + b.x;
+        o.y = (v.y - mean) * rstd * g.y + b.y;
+        o.z = (v.z - mean) * rstd * g.z + b.z;
+        o.w = (v.w - mean) * rstd * g.w + b.w;
+        st4(yr + c, o);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32)
+        Elem<TY>::st(yr + c, (Elem<TX>::ld(xr + c) - mean) * rstd * gamma[c] + beta[c]);
+    }
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat));  dgamma += g*xhat;  dbeta += g.
+// Per-warp column partials live in shared memory ([warps][E] x 2); flushed with one atomicAdd per column
+// per CTA at the end.
+template <typename TX, typename TY, int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TX* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int E) {
+  extern __shared__ __align__(16) float ln_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* pg = ln_smem + (size_t)warp * E;                      // this warp's dgamma partial
+  float* pb = ln_smem + (size_t)(kLnWarps + warp) * E;         // this warp's dbeta partial
+  for (int c = lane; c < E; c += 32) {
+    pg[c] = 0.f;
+    pb[c] = 0.f;
+  }
+  __syncwarp();
+  const float inv_e = 1.f / (float)E;
+  for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+    const TY* gr = dy + (size_t)row * E;
+    const TX* xr = x + (size_t)row * E;
+    TX* dr = dx + (size_t)row * E;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 g = ld4(gr + c), v = ld4(xr + c), w = ld4(gamma + c);
+        const float gw[4] = {g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w};
+        const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s1 += gw[e];
+          s2 = fmaf(gw[e], xh[e], s2);
+        }
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float gw = Elem<TY>::ld(gr + c) * gamma[c], xh = (Elem<TX>::ld(xr + c) - mean) * rstd;
+        s1 += gw;
+        s2 = fmaf(gw, xh, s2);
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_e, c2 = warp_sum(s2) * inv_e;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 g = ld4(gr + c), v = ld4(xr + c), w = ld4(gamma + c);
+        const float gv[4] = {g.x, g.y, g.z, g.w}, wv[4] = {w.x, w.y, w.z, w.w};
+        const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+        float o[4];
+        float4 ag = *reinterpret_cast<float4*>(pg + c), ab = *reinterpret_cast<float4*>(pb + c);
+        float agv[4] = {ag.x, ag.y, ag.z, ag.w}, abv[4] = {ab.x, ab.y, ab.z, ab.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[e] = rstd * (gv[e] * wv[e] - c1 - xh[e] * c2);
+          agv[e] = fmaf(gv[e], xh[e], agv[e]);
+          abv[e] += gv[e];
+        }
+        st4(dr + c, make_float4(o[0], o[1], o[2], o[3]));
+        *reinterpret_cast<float4*>(pg + c) = make_float4(agv[0], agv[1], agv[2], agv[3]);
+        *reinterpret_cast<float4*>(pb + c) = make_float4(abv[0], abv[1], abv[2], abv[3]);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float g = Elem<TY>::ld(gr + c), xh = (Elem<TX>::ld(xr + c) - mean) * rstd;
+        Elem<TX>::st(dr + c, rstd * (g * gamma[c] - c1 - xh * c2));
+        pg[c] = fmaf(g, xh, pg[c]);
+        pb[c] += g;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += kLnWarps * 32) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) {
+      sg += ln_smem[(size_t)w * E + c];
+      sb += ln_smem[(size_t)(kLnWarps + w) * E + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+template <typename TX, typename TY>
+int ln_fwd_t(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int E,
+             float eps, cudaStream_t st) {
+  const int grid = min(ceil_div(M, kLnWarps), 8 * sm_count());
+  if (E % 128 == 0)
+    ln_fwd_kernel<TX, TY, 4><<<grid, kLnWarps * 32, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, M, E, eps);
+  else
+    ln_fwd_kernel<TX, TY, 1><<<grid, kLnWarps * 32, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, M, E, eps);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+template <typename TX, typename TY, int VEC>
+int ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                  float* dgamma, float* dbeta, int M, int E, cudaStream_t st) {
+  const size_t smem = (size_t)2 * kLnWarps * E * sizeof(float);
+  auto kern = ln_bwd_kernel<TX, TY, VEC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const int grid = min(ceil_div(M, kLnWarps), 2 * sm_count());
+  kern<<<grid, kLnWarps * 32, smem, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, dgamma, dbeta, M, E);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+template <typename TX, typename TY>
+int ln_bwd_t(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+             float* dgamma, float* dbeta, int M, int E, cudaStream_t st) {
+  VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
+  VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+  if (E % 128 == 0) return ln_bwd_launch<TX, TY, 4>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
+  return ln_bwd_launch<TX, TY, 1>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
+}
+
+}  // namespace
+
+int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int E,
+                  float eps, int x_dtype, int y_dtype, cudaStream_t st) {
+  VRR_REQUIRE((size_t)2 * kLnWarps * E * sizeof(float) <= 160 * 1024, VRR_ERR_UNSUPPORTED,
+              "layernorm: E = %d too large (max 2560)", E);
+  if (x_dtype == VRR_F32 && y_dtype == VRR_F32) return ln_fwd_t<float, float>(x, gamma, beta, y, mean, rstd, M, E, eps, st);
+  if (x_dtype == VRR_F32 && y_dtype == VRR_BF16) return ln_fwd_t<float, __nv_bfloat16>(x, gamma, beta, y, mean, rstd, M, E, eps, st);
+  if (x_dtype == VRR_BF16 && y_dtype == VRR_BF16)
+    return ln_fwd_t<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, y, mean, rstd, M, E, eps, st);
+  set_error("layernorm_fwd: unsupported dtype combination (x %d, y %d)", x_dtype, y_dtype);
+  return VRR_ERR_UNSUPPORTED;
+}
+
+int layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                  float* dgamma, float* dbeta, int M, int E, int x_dtype, int y_dtype, cudaStream_t st) {
+  VRR_REQUIRE((size_t)2 * kLnWarps * E * sizeof(float) <= 160 * 1024, VRR_ERR_UNSUPPORTED,
+              "layernorm: E = %d too large (max 2560)", E);
+  if (x_dtype == VRR_F32 && y_dtype == VRR_F32) return ln_bwd_t<float, float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
+  if (x_dtype == VRR_F32 && y_dtype == VRR_BF16)
+    return ln_bwd_t<float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
+  if (x_dtype == VRR_BF16 && y_dtype == VRR_BF16)
+    return ln_bwd_t<__nv_bfloat16, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
+  set_error("layernorm_bwd: unsupported dtype combination (x %d, y %d)", x_dtype, y_dtype);
+  return VRR_ERR_UNSUPPORTED;
+}
+
+}  // namespace vrr

@@ -260,4 +260,26 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
                        dtype, (cudaStream_t)stream);
 }
 
+int vrr_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
+                      int E, float eps, int x_dtype, int y_dtype, void* stream) {
+  VRR_REQUIRE(x && gamma && beta && y && mean && rstd, VRR_ERR_INVALID_ARG, "layernorm_fwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(x_dtype) && dtype_ok(y_dtype), VRR_ERR_INVALID_ARG, "layernorm_fwd: bad dtype");
+  VRR_REQUIRE(M > 0 && E > 0, VRR_ERR_INVALID_ARG, "layernorm_fwd: bad sizes");
+  VRR_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, VRR_ERR_INVALID_ARG,
+              "layernorm_fwd: pointers must be 16-byte aligned");
+  if (int rc = require_device()) return rc;
+  return layernorm_fwd(x, gamma, beta, y, mean, rstd, M, E, eps, x_dtype, y_dtype, (cudaStream_t)stream);
+}
+
+int vrr_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      void* dx, float* dgamma, float* dbeta, int M, int E, int x_dtype, int y_dtype, void* stream) {
+  VRR_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, VRR_ERR_INVALID_ARG, "layernorm_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(x_dtype) && dtype_ok(y_dtype), VRR_ERR_INVALID_ARG, "layernorm_bwd: bad dtype");
+  VRR_REQUIRE(M > 0 && E > 0, VRR_ERR_INVALID_ARG, "layernorm_bwd: bad sizes");
+  VRR_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma) & 15) == 0, VRR_ERR_INVALID_ARG,
+              "layernorm_bwd: pointers must be 16-byte aligned");
+  if (int rc = require_device()) return rc;
+  return layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, x_dtype, y_dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

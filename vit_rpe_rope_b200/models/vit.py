@@ -10,8 +10,8 @@ construction (citations: /root/reference/models/vit.py).  What changes is undern
 * qkv Linear + head split + RoPE + cls re-concat    -> one GEMM with RoPE epilogue (vit.py:47-68)
 * QK^T, scale, RPE / Poly-RPE bias, softmax, PV, merge -> one fused attention kernel (vit.py:71-88)
 
-LayerNorm, the output projection, the MLP and the head stay ``torch.nn`` (SURVEY.md section 8(f) rows
-N1-N3: next).  CUDA sm_100 only: CPU inputs raise; there is no fallback path.
+LayerNorm runs the library's fused kernel (first of the "next" rows); the
+output projection, the MLP and the head stay ``torch.nn``.  CUDA sm_100 only: CPU inputs raise; there is no fallback path.
 """
 import torch
 import torch.nn as nn
@@ -91,8 +91,8 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x, freqs_cis=None):
-        x = x + self.drop_path(self.attn(self.norm1(x), freqs_cis=freqs_cis))
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        x = x + self.drop_path(self.attn(ops.layer_norm(x, self.norm1), freqs_cis=freqs_cis))
+        x = x + self.drop_path(self.mlp(ops.layer_norm(x, self.norm2)))
         return x
 
     def set_pos_encoding(self, pos_encoding):
@@ -182,5 +182,6 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x):
         x = self.forward_features(x)
-        x = self.norm(x)
-        return self.head(x[:, 0])
+        # LayerNorm is per token and only the cls token reaches the head (vit.py:284-285): normalising
+        # that row alone gives identical logits and gradients
+        return self.head(ops.layer_norm(x[:, 0], self.norm))

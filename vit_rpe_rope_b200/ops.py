@@ -304,6 +304,61 @@ def fused_attention(planes, scale, bias_mode=_lib.BIAS_NONE, bias_param=None, bi
 
 
 # ------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x) over the last dim, written directly in the consumer's dtype (fp32 statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        _require_cuda(x, weight, bias)
+        lib = _lib.load()
+        E = x.shape[-1]
+        x2 = x.contiguous().view(-1, E)
+        M = x2.shape[0]
+        w32, b32 = _f32c(weight), _f32c(bias)
+        y = torch.empty(M, E, device=x.device, dtype=out_dtype)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _timed("layernorm_fwd"):
+            _lib.check(lib.vrr_layernorm_fwd(_ptr(x2), _ptr(w32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd), M, E,
+                                             float(eps), _DT[x2.dtype], _DT[out_dtype], _stream()),
+                       "vrr_layernorm_fwd")
+        ctx.save_for_backward(x2, w32, mean, rstd)
+        ctx.meta = (x.shape, weight.dtype, bias.dtype, out_dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x2, w32, mean, rstd = ctx.saved_tensors
+        shape, w_dtype, b_dtype, out_dtype = ctx.meta
+        M, E = x2.shape
+        dy2 = dy.contiguous().view(M, E)
+        if dy2.dtype != out_dtype:
+            dy2 = dy2.to(out_dtype)
+        dx = torch.empty_like(x2)
+        dg = torch.empty(E, device=x2.device, dtype=torch.float32)
+        db = torch.empty(E, device=x2.device, dtype=torch.float32)
+        with torch.cuda.device(x2.device), _timed("layernorm_bwd"):
+            _lib.check(lib.vrr_layernorm_bwd(_ptr(dy2), _ptr(x2), _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dg),
+                                             _ptr(db), M, E, _DT[x2.dtype], _DT[out_dtype], _stream()),
+                       "vrr_layernorm_bwd")
+        return dx.view(shape), dg.to(w_dtype), db.to(b_dtype), None, None
+
+
+def layer_norm(x, norm: torch.nn.LayerNorm):
+    """``norm(x)`` for an ``nn.LayerNorm`` over the last dimension, output in the compute dtype
+    (bf16 under autocast: the reference's LayerNorm-then-cast, fused).  Falls through to the module
+    itself for anything that is not a plain affine last-dim LayerNorm (a caller-supplied norm_layer)."""
+    if (type(norm) is not torch.nn.LayerNorm or not norm.elementwise_affine or norm.bias is None
+            or tuple(norm.normalized_shape) != (x.shape[-1],)):
+        return norm(x)
+    out_dtype = compute_dtype(x)
+    if x.dtype == torch.bfloat16 and out_dtype == torch.float32:
+        x = x.float()
+    return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
 class RopeApplyFn(torch.autograd.Function):
     """Stand-alone rotate-half of q and k (public ``apply_rotary_emb``, rope_utils.py:3-37)."""
 
