@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-impl", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-graph", action="store_true", help="issue the training step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -201,13 +202,17 @@ def main():
     import torch.distributed as dist
     from vit_rpe_rope_b200 import VisionTransformer, _lib, ops
     from vit_rpe_rope_b200.dp import BucketedDataParallel
+    from vit_rpe_rope_b200.runtime import GraphedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    use_graph = not args.no_graph
     if world > 1:
+        if use_graph:  # NCCL collectives are captured into the step graph
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     _lib.set_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.attn_impl])
@@ -222,8 +227,10 @@ def main():
     torch.manual_seed(0)
     model = VisionTransformer(**mcfg).to(dev)
     train = wl["train"]
+    use_graph = use_graph and train
     dp = BucketedDataParallel(model, bucket_mb=32.0) if train else None
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True) if train else None
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=use_graph) \
+        if train else None
     if not train:
         model.eval()
 
@@ -232,18 +239,18 @@ def main():
     host_labels = torch.randint(0, mcfg["num_classes"], (batch,), generator=g).pin_memory()
     dev_images, dev_labels = host_images.to(dev), host_labels.to(dev)
 
-    def step(images, labels):
-        if train:
-            dp.zero_grad()
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
-                logits = dp(images)
-                loss = F.cross_entropy(logits.float(), labels)
-            loss.backward()
-            dp.sync()
-            opt.step()
-            return loss
+    runner = None
+    if train:
+        runner = GraphedTrainStep(dp, opt, tuple(host_images.shape), mcfg["num_classes"], dev, bf16=bf16,
+                                  use_graph=use_graph, warmup=max(3, args.warmup))
+        runner.prepare(dev_images, dev_labels)
+
+    def infer(images):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
-            return dp(images) if dp else model(images)
+            return model(images)
+
+    def step_resident():
+        return runner.run() if train else infer(dev_images)
 
     def barrier():
         if world > 1:
@@ -258,11 +265,10 @@ def main():
         return t.item()
 
     for _ in range(args.warmup):
-        step(dev_images, dev_labels)
+        step_resident()
 
-    # ---- timed region 1: device-resident inputs -> `value`, per-launch attention timing -> `roofline`
+    # ---- timed region 1: device-resident inputs -> `value`
     sampler = ClockSampler(local_rank)
-    ops.PROFILE_EVENTS = []
     barrier()
     if rank == 0:
         sampler.start()
@@ -270,32 +276,45 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step(dev_images, dev_labels)
+        step_resident()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    gpu_launches = _lib.launch_count() - launches0
+    gpu_launches = (runner.launches_per_step * args.steps) if (train and use_graph) else _lib.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- per-launch kernel timing (CUDA events on the launching stream) -> `roofline`.  A graph replay has
+    # no host-side launch sites, so the same K steps are issued eagerly once more with events around
+    # every libvrr launch; the kernels and their inputs are identical to the timed region's.
+    ops.PROFILE_EVENTS = []
+    for _ in range(args.steps):
+        runner._eager_step() if train else infer(dev_images)
+    torch.cuda.synchronize()
     events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
     kernel_ms = {}
     for name, a, b in events:
         kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
 
     # ---- timed region 2: end to end through the public API with pinned-host inputs -> `e2e`
+    def step_e2e():
+        if train:
+            runner.load(host_images, host_labels)          # H2D from pinned memory into the static buffers
+            return runner.run().item()                     # D2H read of the step's loss
+        out_ = infer(host_images.to(dev, non_blocking=True))
+        return float(out_.float().cpu()[0, 0])
+
     for _ in range(2):
-        step(host_images.to(dev, non_blocking=True), host_labels.to(dev, non_blocking=True))
+        step_e2e()
     barrier()
     e0.record()
     last = None
     for _ in range(args.steps):
-        imgs = host_images.to(dev, non_blocking=True)
-        lbls = host_labels.to(dev, non_blocking=True)
-        out = step(imgs, lbls)
-        last = out.item() if train else float(out.float().cpu()[0, 0])  # D2H read of the step's result
+        last = step_e2e()
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     h2d = host_images.numel() * host_images.element_size() + host_labels.numel() * host_labels.element_size()
+    out = None if train else infer(dev_images)
 
     if rank != 0:
         if world > 1:
@@ -319,7 +338,8 @@ def main():
         else:
             roofline = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None}
-        roofline.update({"kernel": "vrr_attn_fwd", "avg_launch_ms": avg_ms, "launches_timed": len(kernel_ms["attn_fwd"]),
+        roofline.update({"kernel": "vrr_attn_fwd", "timed": "CUDA events around every launch, eager re-issue of the same K steps",
+                         "avg_launch_ms": avg_ms, "launches_timed": len(kernel_ms["attn_fwd"]),
                          "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts,
                          "tflops": tf, "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
                          "peak_source": peaks["source"] + (" (sustained: kernel timed inside a long step)")})
@@ -341,7 +361,7 @@ def main():
         "config": {"workload": args.workload, **mcfg, "tokens": tokens, "batch_per_gpu": batch,
                    "global_batch": batch * world, "train": train, "optimizer": "AdamW(lr=1e-3, wd=0.01)" if train else None,
                    "parallelism": f"dp{world}", "l2": "inputs+activations per step exceed the 126 MB L2 (no flush needed)",
-                   "attn_impl": args.attn_impl},
+                   "attn_impl": args.attn_impl, "cuda_graph": bool(use_graph)},
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else int(out.numel() * 4)},
         "gpu_launches": int(gpu_launches),

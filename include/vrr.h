@@ -176,6 +176,18 @@ int vrr_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
                       const float* rstd, void* dx, float* dgamma, float* dbeta, int M, int E,
                       int x_dtype, int y_dtype, void* stream);
 
+/* Fused residual add + LayerNorm of the pre-LN block (models/vit.py:122-124: x = x + branch; the next
+ * sub-block starts with norm(x)):  x_new = x + branch (fp32, written);  y = LayerNorm(x_new).
+ * x, x_new fp32 [M][E]; branch `branch_dtype`; y `y_dtype`. */
+int vrr_add_layernorm_fwd(const void* x, const void* branch, void* x_new, const float* gamma,
+                          const float* beta, void* y, float* mean, float* rstd, int M, int E, float eps,
+                          int branch_dtype, int y_dtype, void* stream);
+/* g = d_xnew + LayerNorm'(dy): written as fp32 `dx` (gradient of x) and in `branch_dtype` as `d_branch`
+ * (gradient of branch - the same values); d_xnew may be NULL (no other consumer of x_new). */
+int vrr_add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, void* d_branch, float* dgamma,
+                          float* dbeta, int M, int E, int branch_dtype, int y_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -387,6 +387,35 @@ def test_layernorm_kernel_vs_torch(xdt, ydt, m, e):
     assert err(bs.grad, br.grad) <= tol
 
 
+@pytest.mark.parametrize("bdt,ydt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("m,e", [(5, 48), (130, 192), (515, 768), (3, 100)])
+def test_add_layernorm_kernel_vs_torch(bdt, ydt, m, e):
+    """Fused residual add + LayerNorm: x_new = x + branch, y = LN(x_new); both outputs feed gradients."""
+    g = torch.Generator().manual_seed(e * 3 + m)
+    x = torch.randn(m, e, generator=g) * 1.3
+    br = (torch.randn(m, e, generator=g) * 0.7).to(bdt)
+    w = torch.randn(e, generator=g) * 0.5 + 1.0
+    b = torch.randn(e, generator=g) * 0.2
+    d_xn = torch.randn(m, e, generator=g)
+    d_y = torch.randn(m, e, generator=g).to(ydt)
+    leaves = [t.to(DEV).requires_grad_(True) for t in (x, br, w, b)]
+    x_new, y = ops.AddLayerNormFn.apply(leaves[0], leaves[1], leaves[2], leaves[3], 1e-5, ydt)
+    torch.autograd.backward([x_new, y], [d_xn.to(DEV), d_y.to(DEV)])
+    ref = [t.double().requires_grad_(True) for t in (x, br, w, b)]
+    xn_r = ref[0] + ref[1]
+    y_r = F.layer_norm(xn_r, (e,), ref[2], ref[3], 1e-5)
+    torch.autograd.backward([xn_r, y_r], [d_xn.double(), d_y.double()])
+    exact = bdt == torch.float32 and ydt == torch.float32
+    tol, err = (FP32_TOL, err_scaled) if exact else (BF16_TOL, err_rel)
+    assert err(x_new, xn_r) <= FP32_TOL and x_new.dtype == torch.float32
+    assert err(y.float(), y_r) <= tol
+    assert err(leaves[0].grad, ref[0].grad) <= tol
+    assert err(leaves[1].grad.float(), ref[1].grad) <= tol and leaves[1].grad.dtype == bdt
+    assert err(leaves[2].grad, ref[2].grad) <= (tol if exact else 1e-3 + tol)
+    assert err(leaves[3].grad, ref[3].grad) <= tol
+
+
 @pytest.mark.parametrize("rope", ["axial", "mixed"])
 def test_apply_rotary_emb_public_function(rope):
     b, h, n, d = 2, 3, 16, 32

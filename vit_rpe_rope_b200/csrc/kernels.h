@@ -61,6 +61,13 @@ int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
 int layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
                   float* dgamma, float* dbeta, int M, int E, int x_dtype, int y_dtype, cudaStream_t st);
 
+int add_layernorm_fwd(const void* x, const void* branch, void* x_new, const float* gamma, const float* beta, void* y,
+                      float* mean, float* rstd, int M, int E, float eps, int branch_dtype, int y_dtype,
+                      cudaStream_t st);
+int add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
+                      int branch_dtype, int y_dtype, cudaStream_t st);
+
 // rope.cu
 int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,
                  void* d_qkv, float* d_cos, float* d_sin, int B, int N, int E, int H, int rope_mode, int dtype,

@@ -203,6 +203,201 @@ int ln_bwd_t(const void* dy, const void* x, const float* gamma, const float* mea
   return ln_bwd_launch<TX, TY, 1>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
 }
 
+// ---- fused residual add + LayerNorm (pre-LN transformer: x_new = x + branch; y = LN(x_new)) ----------
+// forward : reads x (fp32) and branch, writes x_new (fp32) and y.
+// backward: dx = d_xnew + LN'(dy) written as fp32 (gradient of the residual input) AND in the branch's
+//           dtype (gradient of the branch: the same values) - the autograd add and the cast disappear.
+template <typename TB, typename TY, int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_ln_fwd_kernel(const float* __restrict__ x, const TB* __restrict__ branch, float* __restrict__ x_new,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, TY* __restrict__ y,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int E, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_e = 1.f / (float)E;
+  for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+    const float* xr = x + (size_t)row * E;
+    const TB* br = branch + (size_t)row * E;
+    float* nr = x_new + (size_t)row * E;
+    TY* yr = y + (size_t)row * E;
+    float s = 0.f;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 a = ld4(xr + c), b = ld4(br + c);
+        const float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        st4(nr + c, v);
+        s += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float v = xr[c] + Elem<TB>::ld(br + c);
+        nr[c] = v;
+        s += v;
+      }
+    }
+    const float mean = warp_sum(s) * inv_e;
+    float q = 0.f;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 a = ld4(xr + c), b = ld4(br + c);
+        const float d0 = a.x + b.x - mean, d1 = a.y + b.y - mean, d2 = a.z + b.z - mean, d3 = a.w + b.w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float d = xr[c] + Elem<TB>::ld(br + c) - mean;
+        q += d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_e + eps);
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 a = ld4(xr + c), b = ld4(br + c), g = ld4(gamma + c), bt = ld4(beta + c);
+        float4 o;
+        o.x = (a.x + b.x - mean) * rstd * g.x + bt.x;
+        o.y = (a.y + b.y - mean) * rstd * g.y + bt.y;
+        o.z = (a.z + b.z - mean) * rstd * g.z + bt.z;
+        o.w = (a.w + b.w - mean) * rstd * g.w + bt.w;
+        st4(yr + c, o);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32)
+        Elem<TY>::st(yr + c, (xr[c] + Elem<TB>::ld(br + c) - mean) * rstd * gamma[c] + beta[c]);
+    }
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+template <typename TB, typename TY, int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_ln_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ d_xnew, const float* __restrict__ x_new,
+                  const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                  const float* __restrict__ rstd_in, float* __restrict__ dx, TB* __restrict__ d_branch,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int E) {
+  extern __shared__ __align__(16) float ln_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* pg = ln_smem + (size_t)warp * E;
+  float* pb = ln_smem + (size_t)(kLnWarps + warp) * E;
+  for (int c = lane; c < E; c += 32) {
+    pg[c] = 0.f;
+    pb[c] = 0.f;
+  }
+  __syncwarp();
+  const float inv_e = 1.f / (float)E;
+  for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+    const TY* gr = dy + (size_t)row * E;
+    const float* xr = x_new + (size_t)row * E;
+    const float* rr = d_xnew ? d_xnew + (size_t)row * E : nullptr;
+    float* dr = dx + (size_t)row * E;
+    TB* br = d_branch + (size_t)row * E;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 g = ld4(gr + c), v = ld4(xr + c), w = ld4(gamma + c);
+        const float gw[4] = {g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w};
+        const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s1 += gw[e];
+          s2 = fmaf(gw[e], xh[e], s2);
+        }
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float gw = Elem<TY>::ld(gr + c) * gamma[c], xh = (xr[c] - mean) * rstd;
+        s1 += gw;
+        s2 = fmaf(gw, xh, s2);
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_e, c2 = warp_sum(s2) * inv_e;
+    if (VEC == 4) {
+      for (int c = lane * 4; c < E; c += 128) {
+        const float4 g = ld4(gr + c), v = ld4(xr + c), w = ld4(gamma + c);
+        const float4 r = rr ? ld4(rr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gv[4] = {g.x, g.y, g.z, g.w}, wv[4] = {w.x, w.y, w.z, w.w}, rv[4] = {r.x, r.y, r.z, r.w};
+        const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+        float o[4];
+        float4 ag = *reinterpret_cast<float4*>(pg + c), ab = *reinterpret_cast<float4*>(pb + c);
+        float agv[4] = {ag.x, ag.y, ag.z, ag.w}, abv[4] = {ab.x, ab.y, ab.z, ab.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[e] = rv[e] + rstd * (gv[e] * wv[e] - c1 - xh[e] * c2);
+          agv[e] = fmaf(gv[e], xh[e], agv[e]);
+          abv[e] += gv[e];
+        }
+        const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+        st4(dr + c, ov);
+        st4(br + c, ov);
+        *reinterpret_cast<float4*>(pg + c) = make_float4(agv[0], agv[1], agv[2], agv[3]);
+        *reinterpret_cast<float4*>(pb + c) = make_float4(abv[0], abv[1], abv[2], abv[3]);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        const float g = Elem<TY>::ld(gr + c), xh = (xr[c] - mean) * rstd;
+        const float o = (rr ? rr[c] : 0.f) + rstd * (g * gamma[c] - c1 - xh * c2);
+        dr[c] = o;
+        Elem<TB>::st(br + c, o);
+        pg[c] = fmaf(g, xh, pg[c]);
+        pb[c] += g;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += kLnWarps * 32) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) {
+      sg += ln_smem[(size_t)w * E + c];
+      sb += ln_smem[(size_t)(kLnWarps + w) * E + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+template <typename TB, typename TY>
+int add_ln_fwd_t(const float* x, const void* branch, float* x_new, const float* gamma, const float* beta, void* y,
+                 float* mean, float* rstd, int M, int E, float eps, cudaStream_t st) {
+  const int grid = min(ceil_div(M, kLnWarps), 8 * sm_count());
+  if (E % 128 == 0)
+    add_ln_fwd_kernel<TB, TY, 4><<<grid, kLnWarps * 32, 0, st>>>(x, (const TB*)branch, x_new, gamma, beta, (TY*)y, mean, rstd, M, E, eps);
+  else
+    add_ln_fwd_kernel<TB, TY, 1><<<grid, kLnWarps * 32, 0, st>>>(x, (const TB*)branch, x_new, gamma, beta, (TY*)y, mean, rstd, M, E, eps);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+template <typename TB, typename TY, int VEC>
+int add_ln_bwd_launch(const void* dy, const float* d_xnew, const float* x_new, const float* gamma, const float* mean,
+                      const float* rstd, float* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
+                      cudaStream_t st) {
+  const size_t smem = (size_t)2 * kLnWarps * E * sizeof(float);
+  auto kern = add_ln_bwd_kernel<TB, TY, VEC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const int grid = min(ceil_div(M, kLnWarps), 2 * sm_count());
+  kern<<<grid, kLnWarps * 32, smem, st>>>((const TY*)dy, d_xnew, x_new, gamma, mean, rstd, dx, (TB*)d_branch, dgamma, dbeta, M, E);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+template <typename TB, typename TY>
+int add_ln_bwd_t(const void* dy, const float* d_xnew, const float* x_new, const float* gamma, const float* mean,
+                 const float* rstd, float* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
+                 cudaStream_t st) {
+  VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
+  VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+  if (E % 128 == 0)
+    return add_ln_bwd_launch<TB, TY, 4>(dy, d_xnew, x_new, gamma, mean, rstd, dx, d_branch, dgamma, dbeta, M, E, st);
+  return add_ln_bwd_launch<TB, TY, 1>(dy, d_xnew, x_new, gamma, mean, rstd, dx, d_branch, dgamma, dbeta, M, E, st);
+}
+
 }  // namespace
 
 int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int E,
@@ -227,6 +422,34 @@ int layernorm_bwd(const void* dy, const void* x, const float* gamma, const float
   if (x_dtype == VRR_BF16 && y_dtype == VRR_BF16)
     return ln_bwd_t<__nv_bfloat16, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
   set_error("layernorm_bwd: unsupported dtype combination (x %d, y %d)", x_dtype, y_dtype);
+  return VRR_ERR_UNSUPPORTED;
+}
+
+int add_layernorm_fwd(const void* x, const void* branch, void* x_new, const float* gamma, const float* beta, void* y,
+                      float* mean, float* rstd, int M, int E, float eps, int branch_dtype, int y_dtype,
+                      cudaStream_t st) {
+  VRR_REQUIRE((size_t)2 * kLnWarps * E * sizeof(float) <= 160 * 1024, VRR_ERR_UNSUPPORTED,
+              "add_layernorm: E = %d too large (max 2560)", E);
+#define ARGS (const float*)x, branch, (float*)x_new, gamma, beta, y, mean, rstd, M, E, eps, st
+  if (branch_dtype == VRR_F32 && y_dtype == VRR_F32) return add_ln_fwd_t<float, float>(ARGS);
+  if (branch_dtype == VRR_BF16 && y_dtype == VRR_BF16) return add_ln_fwd_t<__nv_bfloat16, __nv_bfloat16>(ARGS);
+  if (branch_dtype == VRR_F32 && y_dtype == VRR_BF16) return add_ln_fwd_t<float, __nv_bfloat16>(ARGS);
+#undef ARGS
+  set_error("add_layernorm_fwd: unsupported dtype combination (branch %d, y %d)", branch_dtype, y_dtype);
+  return VRR_ERR_UNSUPPORTED;
+}
+
+int add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
+                      int branch_dtype, int y_dtype, cudaStream_t st) {
+  VRR_REQUIRE((size_t)2 * kLnWarps * E * sizeof(float) <= 160 * 1024, VRR_ERR_UNSUPPORTED,
+              "add_layernorm: E = %d too large (max 2560)", E);
+#define ARGS dy, (const float*)d_xnew, (const float*)x_new, gamma, mean, rstd, (float*)dx, d_branch, dgamma, dbeta, M, E, st
+  if (branch_dtype == VRR_F32 && y_dtype == VRR_F32) return add_ln_bwd_t<float, float>(ARGS);
+  if (branch_dtype == VRR_BF16 && y_dtype == VRR_BF16) return add_ln_bwd_t<__nv_bfloat16, __nv_bfloat16>(ARGS);
+  if (branch_dtype == VRR_F32 && y_dtype == VRR_BF16) return add_ln_bwd_t<float, __nv_bfloat16>(ARGS);
+#undef ARGS
+  set_error("add_layernorm_bwd: unsupported dtype combination (branch %d, y %d)", branch_dtype, y_dtype);
   return VRR_ERR_UNSUPPORTED;
 }
 

@@ -282,4 +282,31 @@ int vrr_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   return layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, x_dtype, y_dtype, (cudaStream_t)stream);
 }
 
+int vrr_add_layernorm_fwd(const void* x, const void* branch, void* x_new, const float* gamma, const float* beta,
+                          void* y, float* mean, float* rstd, int M, int E, float eps, int branch_dtype, int y_dtype,
+                          void* stream) {
+  VRR_REQUIRE(x && branch && x_new && gamma && beta && y && mean && rstd, VRR_ERR_INVALID_ARG, "add_layernorm_fwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(branch_dtype) && dtype_ok(y_dtype), VRR_ERR_INVALID_ARG, "add_layernorm_fwd: bad dtype");
+  VRR_REQUIRE(M > 0 && E > 0, VRR_ERR_INVALID_ARG, "add_layernorm_fwd: bad sizes");
+  VRR_REQUIRE((((uintptr_t)x | (uintptr_t)branch | (uintptr_t)x_new | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+              VRR_ERR_INVALID_ARG, "add_layernorm_fwd: pointers must be 16-byte aligned");
+  if (int rc = require_device()) return rc;
+  return add_layernorm_fwd(x, branch, x_new, gamma, beta, y, mean, rstd, M, E, eps, branch_dtype, y_dtype,
+                           (cudaStream_t)stream);
+}
+
+int vrr_add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, const float* gamma, const float* mean,
+                          const float* rstd, void* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
+                          int branch_dtype, int y_dtype, void* stream) {
+  VRR_REQUIRE(dy && x_new && gamma && mean && rstd && dx && d_branch && dgamma && dbeta, VRR_ERR_INVALID_ARG,
+              "add_layernorm_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(branch_dtype) && dtype_ok(y_dtype), VRR_ERR_INVALID_ARG, "add_layernorm_bwd: bad dtype");
+  VRR_REQUIRE(M > 0 && E > 0, VRR_ERR_INVALID_ARG, "add_layernorm_bwd: bad sizes");
+  VRR_REQUIRE((((uintptr_t)dy | (uintptr_t)d_xnew | (uintptr_t)x_new | (uintptr_t)dx | (uintptr_t)d_branch | (uintptr_t)gamma) & 15) == 0,
+              VRR_ERR_INVALID_ARG, "add_layernorm_bwd: pointers must be 16-byte aligned");
+  if (int rc = require_device()) return rc;
+  return add_layernorm_bwd(dy, d_xnew, x_new, gamma, mean, rstd, dx, d_branch, dgamma, dbeta, M, E, branch_dtype,
+                           y_dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

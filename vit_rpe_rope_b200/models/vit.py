@@ -176,9 +176,29 @@ class VisionTransformer(nn.Module):
         freqs_cis = None
         if self.use_rope:
             freqs_cis = self.pos_embed.get_freqs_cis(h * w, x.device)  # once per forward, all blocks
-        for blk in self.blocks:
-            x = blk(x, freqs_cis=freqs_cis)
+        if not self._fusable(x):
+            for blk in self.blocks:
+                x = blk(x, freqs_cis=freqs_cis)
+            return x
+        # Same arithmetic as the loop above (vit.py:120-125 per block), with every residual add fused with
+        # the LayerNorm that follows it - also across block boundaries:
+        #   x = x + attn(norm1(x));  x = x + mlp(norm2(x))
+        blocks = self.blocks
+        y = ops.layer_norm(x, blocks[0].norm1)
+        for i, blk in enumerate(blocks):
+            x, y = ops.add_layer_norm(x, blk.attn(y, freqs_cis=freqs_cis), blk.norm2)
+            m = blk.mlp(y)
+            if i + 1 < len(blocks):
+                x, y = ops.add_layer_norm(x, m, blocks[i + 1].norm1)
+            else:
+                x = x + m
         return x
+
+    def _fusable(self, x):
+        return len(self.blocks) > 0 and all(
+            type(blk) is Block and isinstance(blk.drop_path, nn.Identity)
+            and ops.can_fuse_add_layer_norm(x, blk.norm1) and ops.can_fuse_add_layer_norm(x, blk.norm2)
+            for blk in self.blocks)
 
     def forward(self, x):
         x = self.forward_features(x)

@@ -345,6 +345,73 @@ class LayerNormFn(torch.autograd.Function):
         return dx.view(shape), dg.to(w_dtype), db.to(b_dtype), None, None
 
 
+class AddLayerNormFn(torch.autograd.Function):
+    """(x_new, y) = (x + branch, LayerNorm(x + branch)): the residual add of one sub-block fused with the
+    LayerNorm that opens the next one; the backward emits the residual-stream gradient (fp32) and the
+    branch gradient (branch dtype) from a single pass."""
+
+    @staticmethod
+    def forward(ctx, x, branch, weight, bias, eps, out_dtype):
+        _require_cuda(x, branch, weight, bias)
+        lib = _lib.load()
+        E = x.shape[-1]
+        x2 = x.contiguous().view(-1, E)
+        b2 = branch.contiguous().view(-1, E)
+        M = x2.shape[0]
+        w32, b32 = _f32c(weight), _f32c(bias)
+        x_new = torch.empty_like(x2)
+        y = torch.empty(M, E, device=x.device, dtype=out_dtype)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _timed("add_layernorm_fwd"):
+            _lib.check(lib.vrr_add_layernorm_fwd(_ptr(x2), _ptr(b2), _ptr(x_new), _ptr(w32), _ptr(b32), _ptr(y),
+                                                 _ptr(mean), _ptr(rstd), M, E, float(eps), _DT[b2.dtype],
+                                                 _DT[out_dtype], _stream()), "vrr_add_layernorm_fwd")
+        ctx.save_for_backward(x_new, w32, mean, rstd)
+        ctx.meta = (x.shape, weight.dtype, bias.dtype, out_dtype, b2.dtype)
+        return x_new.view(x.shape), y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, d_xnew, d_y):
+        lib = _lib.load()
+        x_new, w32, mean, rstd = ctx.saved_tensors
+        shape, w_dtype, b_dtype, out_dtype, br_dtype = ctx.meta
+        M, E = x_new.shape
+        if d_y is None:
+            d_y = torch.zeros(M, E, device=x_new.device, dtype=out_dtype)
+        dy2 = d_y.contiguous().view(M, E)
+        if dy2.dtype != out_dtype:
+            dy2 = dy2.to(out_dtype)
+        dr2 = None
+        if d_xnew is not None:
+            dr2 = d_xnew.contiguous().view(M, E)
+            if dr2.dtype != torch.float32:
+                dr2 = dr2.float()
+        dx = torch.empty_like(x_new)
+        d_branch = torch.empty(M, E, device=x_new.device, dtype=br_dtype)
+        dg = torch.empty(E, device=x_new.device, dtype=torch.float32)
+        db = torch.empty(E, device=x_new.device, dtype=torch.float32)
+        with torch.cuda.device(x_new.device), _timed("add_layernorm_bwd"):
+            _lib.check(lib.vrr_add_layernorm_bwd(_ptr(dy2), _ptr(dr2), _ptr(x_new), _ptr(w32), _ptr(mean), _ptr(rstd),
+                                                 _ptr(dx), _ptr(d_branch), _ptr(dg), _ptr(db), M, E, _DT[br_dtype],
+                                                 _DT[out_dtype], _stream()), "vrr_add_layernorm_bwd")
+        return dx.view(shape), d_branch.view(shape), dg.to(w_dtype), db.to(b_dtype), None, None
+
+
+def can_fuse_add_layer_norm(x, norm) -> bool:
+    """The fused add+LayerNorm kernels need an fp32 residual stream and a plain affine last-dim LayerNorm."""
+    return (x.is_cuda and x.dtype == torch.float32 and type(norm) is torch.nn.LayerNorm and norm.elementwise_affine
+            and norm.bias is not None and tuple(norm.normalized_shape) == (x.shape[-1],))
+
+
+def add_layer_norm(x, branch, norm: torch.nn.LayerNorm):
+    """``x_new = x + branch; y = norm(x_new)`` in one kernel (see :class:`AddLayerNormFn`)."""
+    out_dtype = compute_dtype(x)
+    if branch.dtype not in (torch.float32, out_dtype):
+        branch = branch.to(out_dtype)
+    return AddLayerNormFn.apply(x, branch, norm.weight, norm.bias, norm.eps, out_dtype)
+
+
 def layer_norm(x, norm: torch.nn.LayerNorm):
     """``norm(x)`` for an ``nn.LayerNorm`` over the last dimension, output in the compute dtype
     (bf16 under autocast: the reference's LayerNorm-then-cast, fused).  Falls through to the module
