@@ -30,6 +30,12 @@ int attn_bwd_tc(const void* planes, const vrr_bias_desc* bias, const void* out, 
                 void* d_planes, float* d_bias_param, float* delta, int B, int H, int N, int Dh, float scale,
                 cudaStream_t st);
 
+// attn_bwd_tc2.cu (variant 2: issuer warp, double-buffered 32-row tiles)
+bool attn_bwd_tc2_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
+int attn_bwd_tc2(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out, const float* lse,
+                 void* d_planes, float* d_bias_param, float* delta, int B, int H, int N, int Dh, float scale,
+                 cudaStream_t st);
+
 // gemm_simt.cu
 int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
                       int B, int N, int E, int H, int rope_mode, int dtype, cudaStream_t st);

@@ -21,6 +21,13 @@ namespace {
 
 constexpr int kLnWarps = 8;
 
+// resident CTAs per SM the backward's shared-memory partials allow (2 x warps x E floats per CTA)
+static inline int ln_bwd_ctas_per_sm(int E) {
+  const size_t per_cta = (size_t)2 * kLnWarps * E * sizeof(float) + 1024;
+  int n = (int)((200 * 1024) / per_cta);
+  return n < 1 ? 1 : (n > 6 ? 6 : n);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -188,7 +195,7 @@ int ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float
     VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  const int grid = min(ceil_div(M, kLnWarps), 2 * sm_count());
+  const int grid = min(ceil_div(M, kLnWarps), ln_bwd_ctas_per_sm(E) * sm_count());
   kern<<<grid, kLnWarps * 32, smem, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, dgamma, dbeta, M, E);
   VRR_LAUNCHED();
   return VRR_OK;
@@ -381,7 +388,7 @@ int add_ln_bwd_launch(const void* dy, const float* d_xnew, const float* x_new, c
     VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  const int grid = min(ceil_div(M, kLnWarps), 2 * sm_count());
+  const int grid = min(ceil_div(M, kLnWarps), ln_bwd_ctas_per_sm(E) * sm_count());
   kern<<<grid, kLnWarps * 32, smem, st>>>((const TY*)dy, d_xnew, x_new, gamma, mean, rstd, dx, (TB*)d_branch, dgamma, dbeta, M, E);
   VRR_LAUNCHED();
   return VRR_OK;

@@ -11,6 +11,7 @@ namespace vrr {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_impl{VRR_IMPL_AUTO};
+std::atomic<int> g_bwd_variant{2};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -93,6 +94,7 @@ int vrr_debug_timestamps(void* device_buf) {  /* 64 x int64 device buffer, or NU
 int vrr_set_option(const char* name, int value) {
   if (!name) return VRR_ERR_INVALID_ARG;
   if (!strcmp(name, "attn_fwd_key_tile")) { attn_fwd_tc_set_key_tile(value); return VRR_OK; }
+  if (!strcmp(name, "attn_bwd_variant")) { g_bwd_variant.store(value == 1 ? 1 : 2); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_variant")) { attn_fwd_tc_set_variant(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_smem_pad_kb")) { attn_fwd_tc_set_smem_pad_kb(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
@@ -251,6 +253,9 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
   size_t delta_bytes = (((size_t)B * H * N * sizeof(float) + 255) / 256) * 256;
   float* d_lut = (float*)((char*)workspace + delta_bytes);
   const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && g_bwd_variant.load() == 2 && attn_bwd_tc2_supported(B, H, N, Dh, bias))
+    return attn_bwd_tc2(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
+                        (cudaStream_t)stream);
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_bwd_tc_supported(B, H, N, Dh, bias))
     return attn_bwd_tc(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
                        (cudaStream_t)stream);
