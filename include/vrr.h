@@ -188,6 +188,14 @@ int vrr_add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new,
                           const float* mean, const float* rstd, void* dx, void* d_branch, float* dgamma,
                           float* dbeta, int M, int E, int branch_dtype, int y_dtype, void* stream);
 
+/* Bias gradient of a Linear layer (out-proj vit.py:91, Mlp fc1/fc2 vit.py:118, head vit.py:285):
+ * out[c] = sum_m x[m][c], fp32 [C] (written); x [M][C] `dtype`, C % 4 == 0. */
+int vrr_colsum(const void* x, float* out, int M, int C, int dtype, void* stream);
+/* Backward of the exact (erf) GELU between fc1 and fc2 of the Mlp (vit.py:118, act_layer=nn.GELU):
+ * dh = dy * gelu'(h), written in `dtype`, and db[c] = sum_m dh[m][c] (fp32, written) - the fc1 bias
+ * gradient - in the same pass.  dy, h, dh [M][C]. */
+int vrr_gelu_bwd(const void* dy, const void* h, void* dh, float* db, int M, int C, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -416,6 +416,35 @@ def test_add_layernorm_kernel_vs_torch(bdt, ydt, m, e):
     assert err(leaves[3].grad, ref[3].grad) <= tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,e,hid", [(7, 32, 128), (197 * 3, 192, 768), (130, 96, 100)])
+def test_mlp_and_linear_functions_vs_torch(dtype, m, e, hid):
+    """MlpFn / LinearFn (cuBLAS GEMMs + gelu-backward / column-sum kernels) vs float64 autograd."""
+    g = torch.Generator().manual_seed(m + hid)
+    x = torch.randn(m, e, generator=g).to(dtype)
+    w1, b1 = (torch.randn(hid, e, generator=g) * e ** -0.5).to(dtype), (torch.randn(hid, generator=g) * 0.1).to(dtype)
+    w2, b2 = (torch.randn(e, hid, generator=g) * hid ** -0.5).to(dtype), (torch.randn(e, generator=g) * 0.1).to(dtype)
+    dy = torch.randn(m, e, generator=g).to(dtype)
+    leaves = [t.to(DEV).requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    y = ops.MlpFn.apply(*leaves)
+    y.backward(dy.to(DEV))
+    ref = [t.double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = F.linear(F.gelu(F.linear(ref[0], ref[1], ref[2])), ref[3], ref[4])
+    yr.backward(dy.double())
+    tol, err = (2e-5, err_scaled) if dtype == torch.float32 else (BF16_TOL, err_rel)
+    assert err(y.float(), yr) <= tol
+    for got, want in zip(leaves, ref):
+        assert err(got.grad.float(), want.grad) <= tol
+    lin_leaves = [t.to(DEV).requires_grad_(True) for t in (x, w1, b1)]
+    z = ops.LinearFn.apply(*lin_leaves)
+    dz = torch.randn(m, hid, generator=g).to(dtype)
+    z.backward(dz.to(DEV))
+    lref = [t.double().requires_grad_(True) for t in (x, w1, b1)]
+    F.linear(*lref).backward(dz.double())
+    for got, want in zip(lin_leaves, lref):
+        assert err(got.grad.float(), want.grad) <= tol
+
+
 @pytest.mark.parametrize("rope", ["axial", "mixed"])
 def test_apply_rotary_emb_public_function(rope):
     b, h, n, d = 2, 3, 16, 32

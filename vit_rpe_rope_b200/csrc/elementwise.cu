@@ -1,0 +1,127 @@
+// Reductions / elementwise kernels of the projection and MLP backward (row N1 of SURVEY.md 8(f)):
+//   * colsum: bias gradient db[c] = sum_m dy[m][c]   (ATen's generic reduce ran at ~1.3 TB/s here)
+//   * gelu_bwd_colsum: dh = dy * gelu'(h) (exact erf GELU, timm Mlp / nn.GELU of models/vit.py:118)
+//     with the fc1 bias gradient sum_m dh[m][c] accumulated in the same pass.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vrr {
+
+namespace {
+
+constexpr int kCsThreads = 256;   // 32 column-quads x 8 row lanes
+constexpr int kCsRows = 256;      // rows per CTA
+
+// grid (ceil(C / 128), ceil(M / kCsRows)); thread = 4 consecutive columns x strided rows
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int C) {
+  __shared__ float4 part[8][32];
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + cq * 4;
+  const int r0 = blockIdx.y * kCsRows, r1 = min(M, r0 + kCsRows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float4 v = ld4(x + (size_t)r * C + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = part[k][cq];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(out + c + 0, acc.x);
+    atomicAdd(out + c + 1, acc.y);
+    atomicAdd(out + c + 2, acc.z);
+    atomicAdd(out + c + 3, acc.w);
+  }
+}
+
+__device__ __forceinline__ float gelu_grad(float h) {
+  // d/dh [ 0.5 h (1 + erf(h / sqrt 2)) ] = Phi(h) + h * phi(h),  phi(h) = exp(-h^2/2) / sqrt(2 pi).
+  // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2),
+  // t = 1 / (1 + 0.3275911 z), z = |h| / sqrt 2 - its exponential exp(-z^2) = exp(-h^2/2) is the one
+  // phi(h) needs, so the whole derivative costs one MUFU.EX2, one MUFU.RCP and ~12 FMA-pipe ops
+  // (libm erff alone is ~3x that, which made this kernel issue-bound instead of HBM-bound).
+  const float e = __expf(-0.5f * h * h);
+  const float z = fabsf(h) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.f);           // erf(|h| / sqrt 2)
+  const float cdf = 0.5f * (1.f + copysignf(erf_abs, h));  // Phi(h)
+  return fmaf(h * 0.3989422804014327f, e, cdf);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) gelu_bwd_colsum_kernel(const T* __restrict__ dy, const T* __restrict__ h,
+                                                                     T* __restrict__ dh, float* __restrict__ db, int M,
+                                                                     int C) {
+  __shared__ float4 part[8][32];
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + cq * 4;
+  const int r0 = blockIdx.y * kCsRows, r1 = min(M, r0 + kCsRows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const size_t o = (size_t)r * C + c;
+      const float4 g = ld4(dy + o), hv = ld4(h + o);
+      float4 d;
+      d.x = g.x * gelu_grad(hv.x);
+      d.y = g.y * gelu_grad(hv.y);
+      d.z = g.z * gelu_grad(hv.z);
+      d.w = g.w * gelu_grad(hv.w);
+      st4(dh + o, d);
+      // the bias gradient sums the values as stored (rounded to T), like autograd's sum over dh
+      T q[4];
+      Elem<T>::st(&q[0], d.x); Elem<T>::st(&q[1], d.y); Elem<T>::st(&q[2], d.z); Elem<T>::st(&q[3], d.w);
+      acc.x += Elem<T>::ld(&q[0]); acc.y += Elem<T>::ld(&q[1]); acc.z += Elem<T>::ld(&q[2]); acc.w += Elem<T>::ld(&q[3]);
+    }
+  }
+  part[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = part[k][cq];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(db + c + 0, acc.x);
+    atomicAdd(db + c + 1, acc.y);
+    atomicAdd(db + c + 2, acc.z);
+    atomicAdd(db + c + 3, acc.w);
+  }
+}
+
+}  // namespace
+
+int colsum(const void* x, float* out, int M, int C, int dtype, cudaStream_t st) {
+  VRR_REQUIRE(C % 4 == 0, VRR_ERR_UNSUPPORTED, "colsum: C = %d must be a multiple of 4", C);
+  VRR_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
+  dim3 grid(ceil_div(C, 128), ceil_div(M, kCsRows));
+  if (dtype == VRR_F32) colsum_kernel<float><<<grid, kCsThreads, 0, st>>>((const float*)x, out, M, C);
+  else colsum_kernel<__nv_bfloat16><<<grid, kCsThreads, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+int gelu_bwd_colsum(const void* dy, const void* h, void* dh, float* db, int M, int C, int dtype, cudaStream_t st) {
+  VRR_REQUIRE(C % 4 == 0, VRR_ERR_UNSUPPORTED, "gelu_bwd: C = %d must be a multiple of 4", C);
+  VRR_CUDA(cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st));
+  dim3 grid(ceil_div(C, 128), ceil_div(M, kCsRows));
+  if (dtype == VRR_F32)
+    gelu_bwd_colsum_kernel<float><<<grid, kCsThreads, 0, st>>>((const float*)dy, (const float*)h, (float*)dh, db, M, C);
+  else
+    gelu_bwd_colsum_kernel<__nv_bfloat16><<<grid, kCsThreads, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)h,
+                                                                      (__nv_bfloat16*)dh, db, M, C);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+}  // namespace vrr

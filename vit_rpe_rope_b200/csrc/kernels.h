@@ -74,6 +74,10 @@ int add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, con
                       const float* rstd, void* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
                       int branch_dtype, int y_dtype, cudaStream_t st);
 
+// elementwise.cu
+int colsum(const void* x, float* out, int M, int C, int dtype, cudaStream_t st);
+int gelu_bwd_colsum(const void* dy, const void* h, void* dh, float* db, int M, int C, int dtype, cudaStream_t st);
+
 // rope.cu
 int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,
                  void* d_qkv, float* d_cos, float* d_sin, int B, int N, int E, int H, int rope_mode, int dtype,

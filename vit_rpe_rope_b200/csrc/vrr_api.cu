@@ -314,4 +314,21 @@ int vrr_add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new,
                            y_dtype, (cudaStream_t)stream);
 }
 
+int vrr_colsum(const void* x, float* out, int M, int C, int dtype, void* stream) {
+  VRR_REQUIRE(x && out, VRR_ERR_INVALID_ARG, "colsum: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype) && M > 0 && C > 0, VRR_ERR_INVALID_ARG, "colsum: bad arguments");
+  VRR_REQUIRE(((uintptr_t)x & 15) == 0, VRR_ERR_INVALID_ARG, "colsum: x must be 16-byte aligned");
+  if (int rc = require_device()) return rc;
+  return colsum(x, out, M, C, dtype, (cudaStream_t)stream);
+}
+
+int vrr_gelu_bwd(const void* dy, const void* h, void* dh, float* db, int M, int C, int dtype, void* stream) {
+  VRR_REQUIRE(dy && h && dh && db, VRR_ERR_INVALID_ARG, "gelu_bwd: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype) && M > 0 && C > 0, VRR_ERR_INVALID_ARG, "gelu_bwd: bad arguments");
+  VRR_REQUIRE((((uintptr_t)dy | (uintptr_t)h | (uintptr_t)dh) & 15) == 0, VRR_ERR_INVALID_ARG,
+              "gelu_bwd: pointers must be 16-byte aligned");
+  if (int rc = require_device()) return rc;
+  return gelu_bwd_colsum(dy, h, dh, db, M, C, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

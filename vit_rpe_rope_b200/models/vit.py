@@ -35,6 +35,8 @@ class Mlp(nn.Module):
         self.drop2 = nn.Dropout(drop)
 
     def forward(self, x):
+        if ops.can_fuse_mlp(x, self):
+            return ops.mlp(x, self.fc1, self.fc2)
         return self.drop2(self.fc2(self.drop1(self.act(self.fc1(x)))))
 
 
@@ -70,7 +72,7 @@ class Attention(nn.Module):
             bias_mode, bias_param, bias_grid = _lib.BIAS_POLY, pe.coefficients, pe.grid_size
         planes = ops.qkv_rope(x, self.qkv.weight, cos, sin, self.num_heads)
         out = ops.fused_attention(planes, self.scale, bias_mode, bias_param, bias_grid)
-        return self.proj_drop(self.proj(out))
+        return self.proj_drop(ops.linear(out, self.proj))
 
     def set_pos_encoding(self, pos_encoding):
         self.pos_encoding = pos_encoding  # registers the shared PE module as a child (state_dict dups)
@@ -204,4 +206,4 @@ class VisionTransformer(nn.Module):
         x = self.forward_features(x)
         # LayerNorm is per token and only the cls token reaches the head (vit.py:284-285): normalising
         # that row alone gives identical logits and gradients
-        return self.head(ops.layer_norm(x[:, 0], self.norm))
+        return ops.linear(ops.layer_norm(x[:, 0], self.norm), self.head)

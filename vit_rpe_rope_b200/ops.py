@@ -426,6 +426,95 @@ def layer_norm(x, norm: torch.nn.LayerNorm):
 
 
 # ------------------------------------------------------------------------------------------------
+def _colsum(t2d):
+    lib = _lib.load()
+    M, C = t2d.shape
+    out = torch.empty(C, device=t2d.device, dtype=torch.float32)
+    _lib.check(lib.vrr_colsum(_ptr(t2d), _ptr(out), M, C, _DT[t2d.dtype], _stream()), "vrr_colsum")
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b with the GEMMs on cuBLAS (plain library GEMMs, bias fused in its epilogue) and the
+    bias gradient on the library's column-sum kernel (out-proj / head, models/vit.py:91,285)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        y = torch.nn.functional.linear(x, w, b)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy2 = dy.contiguous().view(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        with torch.cuda.device(dy.device), torch.autocast("cuda", enabled=False):
+            dx = (dy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+            dw = dy2.t() @ x2 if ctx.needs_input_grad[1] else None
+            db = None
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                with _timed("colsum"):
+                    db = _colsum(dy2).to(dy.dtype)
+        return dx, dw, db
+
+
+class MlpFn(torch.autograd.Function):
+    """fc1 -> exact GELU -> fc2 (timm Mlp, models/vit.py:118).  GEMMs on cuBLAS; the backward runs
+    gelu' fused with the fc1 bias-gradient reduction, and the fc2 bias gradient on the column-sum kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        h = torch.nn.functional.linear(x, w1, b1)
+        a = torch.nn.functional.gelu(h)
+        y = torch.nn.functional.linear(a, w2, b2)
+        ctx.save_for_backward(x, h, a, w1, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, h, a, w1, w2 = ctx.saved_tensors
+        dy2 = dy.contiguous().view(-1, dy.shape[-1])
+        x2, h2, a2 = x.reshape(-1, x.shape[-1]), h.view(-1, h.shape[-1]), a.view(-1, a.shape[-1])
+        M, C = h2.shape
+        with torch.cuda.device(dy.device), torch.autocast("cuda", enabled=False):
+            da = dy2 @ w2
+            dw2 = dy2.t() @ a2
+            with _timed("colsum"):
+                db2 = _colsum(dy2).to(dy.dtype)
+            dh = torch.empty_like(h2)
+            db1 = torch.empty(C, device=dy.device, dtype=torch.float32)
+            with _timed("gelu_bwd"):
+                _lib.check(lib.vrr_gelu_bwd(_ptr(da), _ptr(h2), _ptr(dh), _ptr(db1), M, C, _DT[h2.dtype], _stream()),
+                           "vrr_gelu_bwd")
+            dx = (dh @ w1).view(x.shape)
+            dw1 = dh.t() @ x2
+        return dx, dw1, db1.to(dy.dtype), dw2, db2
+
+
+def linear(x, lin: torch.nn.Linear):
+    """``lin(x)`` through :class:`LinearFn` (CUDA, bias, supported dtype, width % 4 == 0) else the module."""
+    if not (x.is_cuda and lin.bias is not None and lin.out_features % 4 == 0 and x.dtype in _DT):
+        return lin(x)
+    dt = compute_dtype(x)
+    return LinearFn.apply(x.to(dt), lin.weight.to(dt), lin.bias.to(dt))
+
+
+def mlp(x, fc1: torch.nn.Linear, fc2: torch.nn.Linear):
+    dt = compute_dtype(x)
+    return MlpFn.apply(x.to(dt), fc1.weight.to(dt), fc1.bias.to(dt), fc2.weight.to(dt), fc2.bias.to(dt))
+
+
+def can_fuse_mlp(x, m) -> bool:
+    act = getattr(m, "act", None)
+    return (x.is_cuda and x.dtype in _DT and type(act) is torch.nn.GELU and getattr(act, "approximate", "none") == "none"
+            and m.fc1.bias is not None and m.fc2.bias is not None and m.fc1.out_features % 4 == 0
+            and m.fc2.out_features % 4 == 0 and getattr(m.drop1, "p", 0.0) == 0.0 and getattr(m.drop2, "p", 0.0) == 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
 class RopeApplyFn(torch.autograd.Function):
     """Stand-alone rotate-half of q and k (public ``apply_rotary_emb``, rope_utils.py:3-37)."""
 
