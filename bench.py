@@ -209,11 +209,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    use_graph = not args.no_graph
+    # CUDA-graph replay of the step is used at world size 1 only.  Capturing the NCCL all-reduce of
+    # BucketedDataParallel inside the graph HUNG at N = 2, 4 and 8 in round-1 testing (cause not
+    # diagnosed), so multi-rank runs issue the step eagerly - the configuration
+    # that was measured at N = 2.
+    use_graph = (not args.no_graph) and world == 1
     if world > 1:
-        if use_graph:  # NCCL collectives are captured into the step graph
-            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        import faulthandler
+        import signal
+        faulthandler.enable()
+        signal.signal(signal.SIGALRM, lambda *_: (sys.stderr.write(
+            "bench.py: multi-rank step stalled for 240 s - aborting instead of hanging\n"), os._exit(3)))
+        signal.alarm(240)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     _lib.load()
     _lib.set_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.attn_impl])
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -316,6 +325,9 @@ def main():
     h2d = host_images.numel() * host_images.element_size() + host_labels.numel() * host_labels.element_size()
     out = None if train else infer(dev_images)
 
+    if world > 1:
+        import signal
+        signal.alarm(0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

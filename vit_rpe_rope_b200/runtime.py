@@ -8,6 +8,10 @@ which already runs the hand-written kernels through the C ABI on the current str
 buffer lives in the graph's private pool, the gradient buckets of ``BucketedDataParallel`` are
 persistent) and replayed with one launch.  Inputs are copied into static device buffers before each
 replay; the loss is read from a static tensor.
+
+Single-process only: capturing the NCCL all-reduce of ``BucketedDataParallel`` in the graph hung at
+2, 4 and 8 ranks in round-1 testing (undiagnosed), so callers pass ``use_graph=False`` when the world
+size is > 1 and the step is issued eagerly.
 """
 import torch
 import torch.nn.functional as F
@@ -42,6 +46,15 @@ class GraphedTrainStep:
     def prepare(self, images, labels):
         """Warm up (allocator, cuBLAS workspaces, one-time kernel attributes) and capture."""
         self.load(images, labels)
+        if not self._use_graph:
+            # eager mode (always the case for world size > 1): warm up on the current stream, exactly
+            # the call sequence of a plain training loop
+            for _ in range(self._warmup):
+                before = _lib.launch_count()
+                self._eager_step()
+                self.launches_per_step = _lib.launch_count() - before
+            torch.cuda.synchronize()
+            return
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
