@@ -220,8 +220,8 @@ def main():
         import signal
         faulthandler.enable()
         signal.signal(signal.SIGALRM, lambda *_: (sys.stderr.write(
-            "bench.py: multi-rank step stalled for 240 s - aborting instead of hanging\n"), os._exit(3)))
-        signal.alarm(240)
+            "bench.py: multi-rank run made no progress for 420 s - aborting instead of hanging\n"), os._exit(3)))
+        signal.alarm(420)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     _lib.load()
     _lib.set_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.attn_impl])
