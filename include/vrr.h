@@ -84,7 +84,13 @@ int vrr_device_ok(void);                   /* 1 if the current device is sm_100,
 int vrr_set_impl(int impl);                /* vrr_impl; process-wide; returns previous value    */
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t vrr_launch_count(void);
-/* Tuning / experiment switches (process-wide).  "attn_fwd_key_tile" = 64 (default) or 128. */
+/* Dispatch counters per kernel family (VRR_IMPL_SIMT or VRR_IMPL_TCGEN05): how many of the entry
+ * points that choose between the two families (patch_embed_fwd, qkv_rope_fwd, attn_fwd, attn_bwd, gemm)
+ * took that family since load.  Lets a caller (and the parity tests) assert which family ran under
+ * VRR_IMPL_AUTO instead of trusting the selection silently. */
+uint64_t vrr_family_count(int family);
+/* Tuning / experiment switches (process-wide): "attn_fwd_table_bulk" (0/1),
+ * "attn_fwd_rescale_threshold_x100". */
 int vrr_set_option(const char* name, int value);
 /* Debug: one CTA of the next attention-forward launches records clock64() phase stamps (8 per key
  * tile, first 8 tiles) into `device_buf` (64 x int64); NULL switches it off. */

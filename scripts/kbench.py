@@ -1,6 +1,6 @@
 """Time the hot-path kernels in isolation at a BASELINE geometry (CUDA events, inputs > L2).
 
-    python scripts/kbench.py [vitb|vitl|x512] [--kt 64|128]
+    python scripts/kbench.py [vitb|vitl|x512]
 """
 import ctypes
 import os
@@ -16,8 +16,6 @@ B, H, N, D = {"vitb": (256, 12, 197, 64), "vitl": (64, 16, 577, 64), "x512": (32
 E = H * D
 dev = "cuda:0"
 lib = _lib.load()
-if "--kt" in sys.argv:
-    lib.vrr_set_option(b"attn_fwd_key_tile", int(sys.argv[sys.argv.index("--kt") + 1]))
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, N, E, generator=g).to(torch.bfloat16).to(dev)
 w = (torch.randn(3 * E, E, generator=g) * E ** -0.5).to(torch.bfloat16).to(dev)

@@ -1,9 +1,18 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
 
 Tolerances (BASELINE.json north_star): index / coordinate tables bit-exact (CPU tests); logits and
-gradients max-abs <= 1e-5 in fp32 and <= 2e-2 relative in bf16.  "max-abs" is scaled by
-max(1, max|reference|) per tensor so that large-magnitude gradients are held to 1e-5 *relative to
-their scale*; "relative" for bf16 is max|a-b| / max|b|.
+gradients max-abs <= 1e-5 in fp32 and <= 2e-2 relative in bf16.
+
+* fp32: ``err_scaled`` = max|a-b| / max(1, max|b|) must be <= 1e-5 (the north-star absolute bar, scaled
+  up only for tensors whose own magnitude exceeds 1), AND - because most gradients are far below 1 in
+  magnitude, where an absolute bar alone is weak - ``err_rel`` = max|a-b| / max|b| must be <=
+  FP32_REL_TOL (summation-order noise of fp32 reductions over 1e3..1e5 terms stays well inside it).
+* bf16: ``err_rel`` <= 2e-2, flat, against the fp32 oracle.  One documented exception class: a tensor
+  for which the REFERENCE's own autocast run is already further than 1e-2 from the fp32 oracle
+  (bf16 rounding noise dominates a small-magnitude gradient) is held to 2x the reference's own error.
+* every bf16 head-dim-64 case asserts that the tcgen05 kernel family ran (``vrr_family_count``).
+
+Observed worst errors are appended to ``gpurun_out/parity_report.txt`` (when that directory exists).
 """
 import ctypes
 import os
@@ -25,8 +34,45 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 MODES = ("none", "absolute", "relative", "polynomial", "rope-axial", "rope-mixed")
 MODEL_TAGS = ["none", "absolute", "relative", "polynomial", "polynomial_perhead", "rope_axial", "rope_mixed"]
 FP32_TOL = 1e-5
+FP32_REL_TOL = 2e-4
 BF16_TOL = 2e-2
 DEV = "cuda:0"
+_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.txt")
+
+
+def report(line):
+    if os.path.isdir(os.path.dirname(_REPORT)):
+        with open(_REPORT, "a") as f:
+            f.write(line + "\n")
+
+
+class tcgen05_must_run:
+    """Context: the wrapped calls must dispatch to the tcgen05 family and never to the SIMT family."""
+
+    def __enter__(self):
+        self.tc0, self.simt0 = _lib.family_count(_lib.IMPL_TCGEN05), _lib.family_count(_lib.IMPL_SIMT)
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is None:
+            assert _lib.family_count(_lib.IMPL_TCGEN05) > self.tc0, "no tcgen05 kernel was dispatched"
+            assert _lib.family_count(_lib.IMPL_SIMT) == self.simt0, "a SIMT kernel ran where tcgen05 was expected"
+        return False
+
+
+def check_fp32(got, want, what=""):
+    ea, er = err_scaled(got, want), err_rel(got, want)
+    report(f"fp32 {what}: scaled {ea:.2e} rel {er:.2e}")
+    assert ea <= FP32_TOL, (what, ea)
+    assert er <= FP32_REL_TOL, (what, er)
+
+
+def check_bf16(got, want32, ref16=None, what=""):
+    e_mine = err_rel(got, want32)
+    e_ref = err_rel(ref16, want32) if ref16 is not None else 0.0
+    bound = BF16_TOL if e_ref <= BF16_TOL / 2 else 2 * e_ref
+    report(f"bf16 {what}: mine {e_mine:.2e} ref-autocast {e_ref:.2e} bound {bound:.2e}")
+    assert e_mine <= bound, (what, e_mine, e_ref)
 
 
 @pytest.fixture(autouse=True, scope="module")
@@ -65,12 +111,12 @@ def test_model_vs_reference_golden_fp32(tag):
     loss = F.cross_entropy(logits, torch.from_numpy(z["labels"]).to(DEV))
     loss.backward()
     assert _lib.launch_count() > before, "no libvrr kernel was launched"
-    assert err_scaled(logits, z["logits"]) <= FP32_TOL
+    check_fp32(logits, z["logits"], f"golden {tag} logits")
     assert abs(loss.item() - float(z["loss"])) <= FP32_TOL
     checked = 0
     for name, p in model.named_parameters():
         assert p.grad is not None, name
-        assert err_scaled(p.grad, z["grad." + name]) <= FP32_TOL, name
+        check_fp32(p.grad, z["grad." + name], f"golden {tag} {name}")
         checked += 1
     assert checked == sum(1 for k in z.files if k.startswith("grad.") and ".attn.pos_encoding." not in k)
 
@@ -99,10 +145,10 @@ def test_attention_module_vs_reference_golden_fp32(tag):
         assert err_scaled(freqs[0], z["cos"]) <= 2e-6 and err_scaled(freqs[1], z["sin"]) <= 2e-6
     y = attn(x, freqs_cis=freqs)
     (y * torch.from_numpy(z["dy"]).to(DEV)).sum().backward()
-    assert err_scaled(y, z["y"]) <= FP32_TOL
-    assert err_scaled(x.grad, z["dx"]) <= FP32_TOL
+    check_fp32(y, z["y"], f"golden attn {tag} y")
+    check_fp32(x.grad, z["dx"], f"golden attn {tag} dx")
     for name, p in attn.named_parameters():
-        assert err_scaled(p.grad, z["grad." + name]) <= FP32_TOL, name
+        check_fp32(p.grad, z["grad." + name], f"golden attn {tag} {name}")
 
 
 # ------------------------------------------------------------------------------------- oracle: ViT-Tiny
@@ -147,9 +193,9 @@ def test_vit_tiny_fp32_vs_oracle(mode, chans):
     logits = model(images.to(DEV))
     F.cross_entropy(logits, labels.to(DEV)).backward()
     want, grads = _oracle_run(kw, sd, images, labels)
-    assert err_scaled(logits, want) <= FP32_TOL
+    check_fp32(logits, want, f"{kw['pos_encoding']} logits")
     for name, p in model.named_parameters():
-        assert err_scaled(p.grad, grads[name]) <= FP32_TOL, name
+        check_fp32(p.grad, grads[name], f"{kw['pos_encoding']} {name}")
 
 
 def test_vit_tiny_polynomial_per_head_fp32():
@@ -162,9 +208,9 @@ def test_vit_tiny_polynomial_per_head_fp32():
     logits = model(images.to(DEV))
     F.cross_entropy(logits, labels.to(DEV)).backward()
     want, grads = _oracle_run(kw, sd, images, labels)
-    assert err_scaled(logits, want) <= FP32_TOL
+    check_fp32(logits, want, f"{kw['pos_encoding']} logits")
     for name, p in model.named_parameters():
-        assert err_scaled(p.grad, grads[name]) <= FP32_TOL, name
+        check_fp32(p.grad, grads[name], f"{kw['pos_encoding']} {name}")
 
 
 @pytest.mark.parametrize("mode", ["none", "absolute", "rope-axial", "rope-mixed"])
@@ -176,9 +222,9 @@ def test_resolution_extrapolation_fp32(mode):
     logits = model(images.to(DEV))
     F.cross_entropy(logits, labels.to(DEV)).backward()
     want, grads = _oracle_run(kw, sd, images, labels)
-    assert err_scaled(logits, want) <= FP32_TOL
+    check_fp32(logits, want, f"{kw['pos_encoding']} logits")
     for name, p in model.named_parameters():
-        assert err_scaled(p.grad, grads[name]) <= FP32_TOL, name
+        check_fp32(p.grad, grads[name], f"{kw['pos_encoding']} {name}")
 
 
 @pytest.mark.parametrize("mode", ["relative", "polynomial"])
@@ -191,29 +237,68 @@ def test_fixed_size_bias_rejects_other_resolutions(mode):
 
 # ------------------------------------------------------------------------------------- bf16 (autocast)
 
+def _bf16_model_case(kw, batch, size, train=True, seed=2):
+    model, sd = _build_pair(kw)
+    torch.manual_seed(seed)
+    images = torch.randn(batch, kw["in_chans"], size, size)
+    labels = torch.randint(0, kw["num_classes"], (batch,))
+    if not train:
+        model.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16), tcgen05_must_run():
+            logits = model(images.to(DEV))
+        cfg = V.VitConfig(**kw)
+        with torch.no_grad():
+            p32 = V.params_from_state_dict(sd, device=DEV, requires_grad=False)
+            want32 = V.forward(cfg, p32, images.to(DEV))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                want16 = V.forward(cfg, p32, images.to(DEV))
+        check_bf16(logits.float(), want32, want16.float(), f"{kw['pos_encoding']} N={(size // kw['patch_size']) ** 2 + 1} logits (eval)")
+        return
+    with tcgen05_must_run():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(images.to(DEV))
+            loss = F.cross_entropy(logits.float(), labels.to(DEV))
+        loss.backward()
+    want32, grads32 = _oracle_run(kw, sd, images, labels, device=DEV)
+    want16, grads16 = _oracle_run(kw, sd, images, labels, device=DEV, autocast=True)
+    tag = f"{kw['pos_encoding']} E={kw['embed_dim']} N={(size // kw['patch_size']) ** 2 + 1}"
+    check_bf16(logits.float(), want32, want16.float(), f"{tag} logits")
+    for name, p in model.named_parameters():
+        assert p.grad.dtype == torch.float32
+        check_bf16(p.grad, grads32[name], grads16[name], f"{tag} {name}")
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_vit_bf16_autocast_vs_reference_semantics(mode):
     """bf16 = the reference ops under torch.autocast('cuda', bfloat16) with fp32 master weights
-    (SURVEY row O4).  Head dim 64 (ViT-B geometry, shortened) so the tcgen05 kernels are the ones
-    exercised when the library selects them.  Error is measured against the fp32 oracle and must be
-    within 2e-2 relative of it, and not worse than 3x the reference-autocast path's own error."""
+    (SURVEY row O4).  Head dim 64 (ViT-B geometry, shortened): the tcgen05 kernels must be the ones
+    that run.  Logits and every gradient within 2e-2 relative of the fp32 oracle (see module docstring)."""
     kw = dict(img_size=64, patch_size=8, in_chans=3, num_classes=10, embed_dim=256, depth=2, num_heads=4,
               pos_encoding=mode)
-    model, sd = _build_pair(kw)
-    torch.manual_seed(2)
-    images, labels = torch.randn(16, 3, 64, 64), torch.randint(0, 10, (16,))
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        logits = model(images.to(DEV))
-        loss = F.cross_entropy(logits.float(), labels.to(DEV))
-    loss.backward()
-    want32, grads32 = _oracle_run(kw, sd, images, labels, device=DEV)
-    want16, grads16 = _oracle_run(kw, sd, images, labels, device=DEV, autocast=True)
-    e_mine, e_ref = err_rel(logits.float(), want32), err_rel(want16.float(), want32)
-    assert e_mine <= BF16_TOL and e_mine <= 3 * e_ref + 2e-3, (e_mine, e_ref)
-    for name, p in model.named_parameters():
-        e_mine, e_ref = err_rel(p.grad, grads32[name]), err_rel(grads16[name], grads32[name])
-        assert p.grad.dtype == torch.float32
-        assert e_mine <= max(BF16_TOL, 3 * e_ref), (name, e_mine, e_ref)
+    _bf16_model_case(kw, batch=16, size=64)
+
+
+@pytest.mark.parametrize("mode", ["rope-mixed", "relative", "polynomial"])
+def test_cfg3_geometry_bf16(mode):
+    """BASELINE configs[2] geometry (ViT-B/16-224: 12 heads x 64, 197 tokens, E 768), depth 2, batch 4."""
+    kw = dict(img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=2, num_heads=12,
+              pos_encoding=mode)
+    _bf16_model_case(kw, batch=4, size=224)
+
+
+def test_cfg4_geometry_bf16():
+    """BASELINE configs[3] geometry (ViT-L/16-384: 16 heads x 64, 577 tokens, E 1024, rope-axial), depth 1."""
+    kw = dict(img_size=384, patch_size=16, in_chans=3, num_classes=1000, embed_dim=1024, depth=1, num_heads=16,
+              pos_encoding="rope-axial")
+    _bf16_model_case(kw, batch=2, size=384)
+
+
+def test_cfg5_resolution_extrapolation_inference_bf16():
+    """BASELINE configs[4]: ViT-B/16 rope-mixed built at 224, fed 512x512 (1025 tokens), eval + no_grad
+    (reference resolution path: models/vit.py:249,265)."""
+    kw = dict(img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=2, num_heads=12,
+              pos_encoding="rope-mixed")
+    _bf16_model_case(kw, batch=2, size=512, train=False)
 
 
 # ------------------------------------------------------------------------------------- kernels vs numpy
@@ -241,24 +326,29 @@ def _bias_case(kind, h, n, seed=0):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("n,d", [(1, 16), (2, 32), (17, 16), (65, 32), (65, 64), (197, 64), (200, 64), (257, 64)])
+@pytest.mark.parametrize("n,d", [(1, 16), (2, 32), (17, 16), (65, 32), (65, 64), (197, 64), (200, 64), (257, 64),
+                                 (577, 64), (1025, 64)])
 @pytest.mark.parametrize("kind", ["none", "table", "poly", "poly_perhead"])
 def test_attention_kernels_vs_numpy(dtype, n, d, kind):
-    """Fused attention fwd + bwd (whatever kernel family the library selects) vs float64 numpy,
-    ragged and edge sizes: N = 1, N not a multiple of any tile, N > one tile."""
+    """Fused attention fwd + bwd vs float64 numpy, ragged and edge sizes: N = 1, N not a multiple of any
+    tile, N > one tile, and the cfg4 / cfg5 sequence lengths (577 = 10 key tiles, 1025 = 17: every
+    K/V ring stage and mbarrier parity wraps several times).  bf16 with head dim 64 must take the
+    tcgen05 family."""
     if kind.startswith("poly") and int(round((n - 1) ** 0.5)) ** 2 != n - 1:
         pytest.skip("polynomial bias needs a square patch grid")
     if kind.startswith("poly") and n == 1:
         pytest.skip("no patches")
-    b, h = 2, 3
+    b, h = (2, 3) if n <= 257 else (1, 2)
     mode, param, grid, bias_np = _bias_case(kind, h, n)
     planes = _planes(b, h, n, d, dtype).to(DEV).requires_grad_(True)
     prm = None if param is None else param.to(DEV).requires_grad_(True)
     scale = d ** -0.5
-    out = ops.fused_attention(planes, scale, mode, prm, grid)
     g = torch.Generator().manual_seed(9)
     d_out = torch.randn(b, n, h * d, generator=g).to(dtype)
-    out.backward(d_out.to(DEV))
+    import contextlib
+    with (tcgen05_must_run() if (dtype == torch.bfloat16 and d == 64) else contextlib.nullcontext()):
+        out = ops.fused_attention(planes, scale, mode, prm, grid)
+        out.backward(d_out.to(DEV))
     pl = planes.detach().double().cpu().numpy()
     o_np, _, _, _ = A.attention_forward(pl[0], pl[1], pl[2], scale, bias_np)
     # the backward re-reads the STORED output (bf16-rounded in bf16 mode) for delta = rowsum(dO*O)
@@ -272,7 +362,12 @@ def test_attention_kernels_vs_numpy(dtype, n, d, kind):
     if kind == "table":
         assert e(prm.grad, A.dtable_from_dbias(gr["dbias"])) <= tol
     if kind.startswith("poly"):
-        assert e(prm.grad, A.dcoef_from_dbias(gr["dbias"], 3, shared=(kind == "poly"))) <= 5 * tol
+        # d_coef[k] = sum over B*H*N^2 terms of dS * d^k: for k = 3 the terms are ~1e4 x larger than the
+        # bf16-rounded dS noise of the k = 0 column, all summed into one [..,4] tensor whose max is the
+        # k = 3 entry -> a 2x allowance in bf16; flat in fp32
+        e_c = e(prm.grad, A.dcoef_from_dbias(gr["dbias"], 3, shared=(kind == "poly")))
+        report(f"attn kernel {dtype} n={n} {kind}: d_coef err {e_c:.2e}")
+        assert e_c <= (tol if dtype == torch.float32 else 2 * tol)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -324,11 +419,13 @@ def test_qkv_rope_kernel_vs_numpy(dtype, rope, b, n, e, h):
         dq[:, :, 1:] = A.rotate_half_inverse(gpl[0][:, :, 1:], c, s)
         dk[:, :, 1:] = A.rotate_half_inverse(gpl[1][:, :, 1:], c, s)
         red = (0,) if rope == "mixed" else (0, 1)
-        assert e_(cs.grad, dc.sum(red)) <= 5 * tol
-        assert e_(sn.grad, ds_.sum(red)) <= 5 * tol
+        e_c, e_s = e_(cs.grad, dc.sum(red)), e_(sn.grad, ds_.sum(red))
+        report(f"qkv_rope {dtype} {rope} b={b} n={n} e={e}: d_cos {e_c:.2e} d_sin {e_s:.2e}")
+        assert e_c <= tol and e_s <= tol
     dqkv = np.stack([dq, dk, dv]).transpose(1, 3, 0, 2, 4).reshape(b * n, 3 * e)
-    assert e_(xs.grad.float(), (dqkv @ wd).reshape(b, n, e)) <= tol
-    assert e_(ws.grad.float(), dqkv.T @ xd.reshape(b * n, e)) <= (tol if dtype == torch.float32 else 2 * tol)
+    e_x, e_w = e_(xs.grad.float(), (dqkv @ wd).reshape(b, n, e)), e_(ws.grad.float(), dqkv.T @ xd.reshape(b * n, e))
+    report(f"qkv_rope {dtype} {rope} b={b} n={n} e={e}: dx {e_x:.2e} dw {e_w:.2e}")
+    assert e_x <= tol and e_w <= tol
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

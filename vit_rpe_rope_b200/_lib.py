@@ -36,6 +36,7 @@ SIGNATURES = {
     "vrr_device_ok": (c_int, []),
     "vrr_set_impl": (c_int, [c_int]),
     "vrr_launch_count": (c_uint64, []),
+    "vrr_family_count": (c_uint64, [c_int]),
     "vrr_set_option": (c_int, [c_char_p, c_int]),
     "vrr_debug_timestamps": (c_int, [c_void_p]),
     "vrr_patch_embed_workspace_bytes": (c_size_t, [c_int] * 7),
@@ -96,6 +97,11 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().vrr_launch_count())
+
+
+def family_count(family: int) -> int:
+    """Dispatches that took the SIMT (IMPL_SIMT) or tcgen05 (IMPL_TCGEN05) kernel family since load."""
+    return int(load().vrr_family_count(int(family)))
 
 
 def set_impl(impl: int) -> int:

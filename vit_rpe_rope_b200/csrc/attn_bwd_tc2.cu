@@ -607,14 +607,8 @@ int attn_bwd_tc2(const void* planes, const vrr_bias_desc* bias, const void* out,
   const size_t smem_kv = bwd2_smem_bytes(N, bias, &p.lut_floats, true);
 #define LAUNCH(MODE)                                                                                             \
   do {                                                                                                           \
-    static bool attr_set = false;                                                                                \
-    if (!attr_set) {                                                                                             \
-      VRR_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                    110 * 1024));                                                                \
-      VRR_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    110 * 1024));                                                                \
-      attr_set = true;                                                                                           \
-    }                                                                                                            \
+    VRR_SMEM_ATTR_ONCE(attn_bwd_dq_tc2_kernel<MODE>, 110 * 1024);                                                \
+    VRR_SMEM_ATTR_ONCE(attn_bwd_dkv_tc2_kernel<MODE>, 110 * 1024);                                               \
     attn_bwd_dq_tc2_kernel<MODE><<<grid, kThreads, smem_q, st>>>(tm_pl, tm_do, p);                               \
     VRR_LAUNCHED();                                                                                              \
     attn_bwd_dkv_tc2_kernel<MODE><<<grid, kThreads, smem_kv, st>>>(tm_pl, tm_do, p);                             \

@@ -41,8 +41,19 @@ extern std::atomic<int> g_impl;
     VRR_CUDA(cudaGetLastError());                        \
   } while (0)
 
-int require_device();  // VRR_OK or VRR_ERR_NO_DEVICE
-int sm_count();
+int require_device();  // VRR_OK or VRR_ERR_NO_DEVICE (state cached per device ordinal)
+int sm_count();        // SM count of the current device
+extern std::atomic<uint64_t> g_family_launches[3];  // indexed by vrr_impl: dispatches per kernel family
+bool first_use_on_device(std::atomic<unsigned char>* flags);  // flags: static array [64], one per device
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device).
+#define VRR_SMEM_ATTR_ONCE(kernel, bytes)                                                              \
+  do {                                                                                                 \
+    static std::atomic<unsigned char> flags__[64];                                                     \
+    if (::vrr::first_use_on_device(flags__))                                                           \
+      VRR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+  } while (0)
+#define VRR_COUNT_FAMILY(f) ::vrr::g_family_launches[(f)].fetch_add(1, std::memory_order_relaxed)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

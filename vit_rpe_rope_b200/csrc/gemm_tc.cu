@@ -225,11 +225,7 @@ int launch_gemm_tc(const void* a, const void* bw, int M, int Nout, int K, const 
   g.tiles_n = Nout / BN;
   g.num_k = K / kBK;
   const size_t smem = 1024 + (size_t)kGemmStages * (kATileBytes + BN * kBK * 2) + (2 * kGemmStages + 4) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VRR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  VRR_SMEM_ATTR_ONCE((gemm_tc_kernel<BN, Epi>), smem);
   const int grid = min(sm_count(), g.tiles_m * g.tiles_n);
   gemm_tc_kernel<BN, Epi><<<grid, 192, smem, st>>>(ta, tb, g, epi);
   VRR_LAUNCHED();

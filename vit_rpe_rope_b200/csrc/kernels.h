@@ -15,20 +15,11 @@ int attn_bwd_simt(const void* planes, const vrr_bias_desc* bias, const void* out
 
 // attn_tc.cu (tcgen05 / TMEM, bf16, Dh == 64)
 bool attn_fwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
-void attn_fwd_tc_set_key_tile(int kt);
-void attn_fwd_tc_set_variant(int v);
 void attn_fwd_tc_set_threshold_x100(int v);
 void attn_fwd_tc_set_table_bulk(int v);
-void attn_fwd_tc_set_smem_pad_kb(int v);
 void attn_fwd_tc_set_debug(long long* buf);
 int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
                 int Dh, float scale, cudaStream_t st);
-
-// attn_bwd_tc.cu (tcgen05 / TMEM, bf16, Dh == 64)
-bool attn_bwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
-int attn_bwd_tc(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out, const float* lse,
-                void* d_planes, float* d_bias_param, float* delta, int B, int H, int N, int Dh, float scale,
-                cudaStream_t st);
 
 // attn_bwd_tc2.cu (variant 2: issuer warp, double-buffered 32-row tiles)
 bool attn_bwd_tc2_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);

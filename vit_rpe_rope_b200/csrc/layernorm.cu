@@ -190,11 +190,7 @@ int ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float
                   float* dgamma, float* dbeta, int M, int E, cudaStream_t st) {
   const size_t smem = (size_t)2 * kLnWarps * E * sizeof(float);
   auto kern = ln_bwd_kernel<TX, TY, VEC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  VRR_SMEM_ATTR_ONCE(kern, 160 * 1024);
   const int grid = min(ceil_div(M, kLnWarps), ln_bwd_ctas_per_sm(E) * sm_count());
   kern<<<grid, kLnWarps * 32, smem, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, dgamma, dbeta, M, E);
   VRR_LAUNCHED();
@@ -383,11 +379,7 @@ int add_ln_bwd_launch(const void* dy, const float* d_xnew, const float* x_new, c
                       cudaStream_t st) {
   const size_t smem = (size_t)2 * kLnWarps * E * sizeof(float);
   auto kern = add_ln_bwd_kernel<TB, TY, VEC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  VRR_SMEM_ATTR_ONCE(kern, 160 * 1024);
   const int grid = min(ceil_div(M, kLnWarps), ln_bwd_ctas_per_sm(E) * sm_count());
   kern<<<grid, kLnWarps * 32, smem, st>>>((const TY*)dy, d_xnew, x_new, gamma, mean, rstd, dx, (TB*)d_branch, dgamma, dbeta, M, E);
   VRR_LAUNCHED();

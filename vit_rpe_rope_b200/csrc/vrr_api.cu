@@ -11,7 +11,6 @@ namespace vrr {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_impl{VRR_IMPL_AUTO};
-std::atomic<int> g_bwd_variant{2};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,11 +19,23 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_dev_checked = -1;  // -1 unknown, 0 bad, 1 ok (per process; one device per process)
-static int g_sms = 148;
+// Per-DEVICE state (a process may drive several GPUs): 0 unknown, 1 ok, -1 not sm_100.  Plain
+// atomics: racing first calls on one device compute the same values.
+constexpr int kMaxDevices = 64;
+static std::atomic<int> g_dev_state[kMaxDevices];
+static std::atomic<int> g_dev_sms[kMaxDevices];
+std::atomic<uint64_t> g_family_launches[3];  // [VRR_IMPL_SIMT], [VRR_IMPL_TCGEN05] dispatch counters
+
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return dev;
+}
 
 int require_device() {
-  if (g_dev_checked == 1) return VRR_OK;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {
@@ -32,24 +43,42 @@ int require_device() {
     set_error("no CUDA device: %s", cudaGetErrorString(e));
     return VRR_ERR_NO_DEVICE;
   }
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
+  if (dev < 0 || dev >= kMaxDevices) {
+    set_error("device ordinal %d out of range", dev);
+    return VRR_ERR_NO_DEVICE;
+  }
+  const int state = g_dev_state[dev].load(std::memory_order_acquire);
+  if (state == 1) return VRR_OK;
+  int major = 0, minor = 0, sms = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
     return VRR_ERR_NO_DEVICE;
   }
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; libvrr_b200 is built for sm_100a only (no fallback path)", dev,
-              prop.major, prop.minor);
-    g_dev_checked = 0;
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; libvrr_b200 is built for sm_100a only (no fallback path)", dev, major, minor);
+    g_dev_state[dev].store(-1, std::memory_order_release);
     return VRR_ERR_NO_DEVICE;
   }
-  g_sms = prop.multiProcessorCount;
-  g_dev_checked = 1;
+  g_dev_sms[dev].store(sms, std::memory_order_relaxed);
+  g_dev_state[dev].store(1, std::memory_order_release);
   return VRR_OK;
 }
-int sm_count() { return g_sms; }
+int sm_count() {
+  const int dev = current_device();
+  const int n = (dev >= 0 && dev < kMaxDevices) ? g_dev_sms[dev].load(std::memory_order_relaxed) : 0;
+  return n > 0 ? n : 148;
+}
+
+// One-time per (kernel, device) attribute set-up: `flags` is a function-local static array.
+bool first_use_on_device(std::atomic<unsigned char>* flags) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  return flags[dev].exchange(1, std::memory_order_acq_rel) == 0;
+}
 
 static bool dtype_ok(int d) { return d == VRR_F32 || d == VRR_BF16; }
 static bool dh_ok(int dh) { return dh == 16 || dh == 32 || dh == 64; }
@@ -87,16 +116,16 @@ int vrr_set_impl(int impl) {
   return g_impl.exchange(impl);
 }
 uint64_t vrr_launch_count(void) { return g_launches.load(); }
+uint64_t vrr_family_count(int family) {
+  if (family != VRR_IMPL_SIMT && family != VRR_IMPL_TCGEN05) return 0;
+  return g_family_launches[family].load();
+}
 int vrr_debug_timestamps(void* device_buf) {  /* 64 x int64 device buffer, or NULL to switch off */
   attn_fwd_tc_set_debug((long long*)device_buf);
   return VRR_OK;
 }
 int vrr_set_option(const char* name, int value) {
   if (!name) return VRR_ERR_INVALID_ARG;
-  if (!strcmp(name, "attn_fwd_key_tile")) { attn_fwd_tc_set_key_tile(value); return VRR_OK; }
-  if (!strcmp(name, "attn_bwd_variant")) { g_bwd_variant.store(value == 1 ? 1 : 2); return VRR_OK; }
-  if (!strcmp(name, "attn_fwd_variant")) { attn_fwd_tc_set_variant(value); return VRR_OK; }
-  if (!strcmp(name, "attn_fwd_smem_pad_kb")) { attn_fwd_tc_set_smem_pad_kb(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_rescale_threshold_x100")) { attn_fwd_tc_set_threshold_x100(value); return VRR_OK; }
   set_error("vrr_set_option: unknown option '%s'", name);
@@ -123,11 +152,15 @@ int vrr_patch_embed_fwd(const void* images, const void* weight, const void* bias
     VRR_REQUIRE(workspace && workspace_bytes >= need, VRR_ERR_WORKSPACE,
                 "patch_embed_fwd: workspace %zu < %zu bytes (vrr_patch_embed_workspace_bytes)", workspace_bytes, need);
     VRR_REQUIRE(((uintptr_t)workspace & 255) == 0, VRR_ERR_INVALID_ARG, "patch_embed_fwd: workspace must be 256-byte aligned");
+    VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
     if (int rc = patch_embed_fwd_tc(images, weight, bias, pos_embed, tokens, workspace, B, C, Hi, Wi, P, E, img_dtype,
                                     tok_dtype, (cudaStream_t)stream))
       return rc;
     return patch_cls_rows(tokens, cls_token, B, (Hi / P) * (Wi / P), E, tok_dtype, (cudaStream_t)stream);
   }
+  VRR_REQUIRE(impl != VRR_IMPL_TCGEN05 || dtype != VRR_BF16, VRR_ERR_UNSUPPORTED,
+              "patch_embed_fwd: tcgen05 kernel forced but shape unsupported (P %% 8, C*P*P %% 64, E %% 64)");
+  VRR_COUNT_FAMILY(VRR_IMPL_SIMT);
   return patch_embed_fwd_simt(images, weight, bias, cls_token, pos_embed, tokens, B, C, Hi, Wi, P, E, img_dtype, dtype,
                               tok_dtype, (cudaStream_t)stream);
 }
@@ -165,10 +198,13 @@ int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, con
   VRR_REQUIRE(dh_ok(E / H), VRR_ERR_UNSUPPORTED, "qkv_rope_fwd: head dim %d unsupported (16, 32, 64)", E / H);
   if (int rc = require_device()) return rc;
   const int impl = g_impl.load();
-  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && qkv_rope_fwd_tc_supported(B, N, E, H))
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && qkv_rope_fwd_tc_supported(B, N, E, H)) {
+    VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
     return qkv_rope_fwd_tc(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
+  }
   VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
               "qkv_rope_fwd: tcgen05 kernel forced but shape/dtype unsupported (bf16, Dh=64, E%%64==0)");
+  VRR_COUNT_FAMILY(VRR_IMPL_SIMT);
   return qkv_rope_fwd_simt(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, dtype, (cudaStream_t)stream);
 }
 
@@ -221,10 +257,13 @@ int vrr_attn_fwd(const void* planes, const vrr_bias_desc* bias, void* out, float
   if (int rc = check_bias(bias, H, N)) return rc;
   if (int rc = require_device()) return rc;
   const int impl = g_impl.load();
-  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_fwd_tc_supported(B, H, N, Dh, bias))
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_fwd_tc_supported(B, H, N, Dh, bias)) {
+    VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
     return attn_fwd_tc(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
+  }
   VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
               "attn_fwd: tcgen05 kernel forced but shape/dtype unsupported (bf16, Dh=64)");
+  VRR_COUNT_FAMILY(VRR_IMPL_SIMT);
   return attn_fwd_simt(planes, bias, out, lse, B, H, N, Dh, scale, dtype, (cudaStream_t)stream);
 }
 
@@ -253,14 +292,16 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
   size_t delta_bytes = (((size_t)B * H * N * sizeof(float) + 255) / 256) * 256;
   float* d_lut = (float*)((char*)workspace + delta_bytes);
   const int impl = g_impl.load();
-  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && g_bwd_variant.load() == 2 && attn_bwd_tc2_supported(B, H, N, Dh, bias))
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_bwd_tc2_supported(B, H, N, Dh, bias)) {
+    VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
     return attn_bwd_tc2(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
                         (cudaStream_t)stream);
-  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_bwd_tc_supported(B, H, N, Dh, bias))
-    return attn_bwd_tc(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
-                       (cudaStream_t)stream);
+  }
+  // e.g. polynomial degree > 3 (the tcgen05 kernel keeps 4 power sums per thread): explicit under
+  // VRR_IMPL_TCGEN05, and visible to AUTO callers through vrr_family_count(VRR_IMPL_SIMT)
   VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
               "attn_bwd: tcgen05 kernel forced but shape/dtype unsupported (bf16, Dh=64, poly degree <= 3)");
+  VRR_COUNT_FAMILY(VRR_IMPL_SIMT);
   return attn_bwd_simt(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, d_lut, B, H, N, Dh, scale,
                        dtype, (cudaStream_t)stream);
 }
