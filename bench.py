@@ -73,6 +73,8 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip timing the reference's eager PyTorch path (oracle port) on the same GPU")
     ap.add_argument("--attn-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-graph", action="store_true", help="issue the training step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -88,6 +90,16 @@ def load_peaks():
         return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
                     bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def load_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the hot-path kernels, taken
+    from the committed `ncu --set full` capture summarised in profiles/traffic.json (keyed by workload)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 class ClockSampler:
@@ -174,6 +186,51 @@ def cpu_reference_run(wl, steps, warmup):
                        f"torch {torch.__version__} CPU, {threads} threads"), dt / steps * 1e3
 
 
+def gpu_reference_run(wl, batch, dev, steps, warmup):
+    """The reference's own eager PyTorch path (oracle port: the same torch ops in the same order) on THIS
+    GPU at the workload's full batch and dtype (bf16 = torch.autocast, fp32 master weights) - the bar a
+    user of the reference on a B200 would see (train.py:108-116 with device='cuda').  A baseline like
+    cpu_baseline: reported, never on the product path."""
+    from oracle import vit_torch as V
+    cfg = V.VitConfig(**wl["model"])
+    size = wl.get("input_size", cfg.img_size)
+    bf16 = wl["dtype"] == "bf16"
+    try:
+        params = V.params_from_state_dict(V.init_state_dict(cfg, seed=0), requires_grad=wl["train"], device=dev)
+        g = torch.Generator().manual_seed(0)
+        images = torch.randn(batch, cfg.in_chans, size, size, generator=g).to(dev)
+        labels = torch.randint(0, cfg.num_classes, (batch,), generator=g).to(dev)
+        opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=1e-3, weight_decay=0.01, fused=True) \
+            if wl["train"] else None
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+                if wl["train"]:
+                    opt.zero_grad()
+                    loss = F.cross_entropy(V.forward(cfg, params, images).float(), labels)
+                    loss.backward()
+                    opt.step()
+                else:
+                    with torch.no_grad():
+                        V.forward(cfg, params, images)
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+                "kind": "port of the reference's eager path (oracle/vit_torch.py) on the same B200, "
+                        + ("bf16 autocast" if bf16 else "fp32 (TF32 off)") + ", eager launches, torch " + torch.__version__}
+    except torch.OutOfMemoryError as e:  # pragma: no cover
+        return {"unavailable": f"out of memory at batch {batch}: {str(e)[:80]}"}
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -209,20 +266,19 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # CUDA-graph replay of the step is used at world size 1 only.  Capturing the NCCL all-reduce of
-    # BucketedDataParallel inside the graph HUNG at N = 2, 4 and 8 in round-1 testing (cause not
-    # diagnosed), so multi-rank runs issue the step eagerly - the configuration
-    # that was measured at N = 2.
-    use_graph = (not args.no_graph) and world == 1
+    # The step (incl. the bucketed NCCL all-reduces) is captured into one CUDA graph at every world size.
+    # Round 1's multi-rank captures worked; what stalled was process-group teardown with the graph still
+    # alive - see teardown() below.
+    use_graph = not args.no_graph
     if world > 1:
         import datetime
         import faulthandler
         import signal
         faulthandler.enable()
         signal.signal(signal.SIGALRM, lambda *_: (sys.stderr.write(
-            "bench.py: multi-rank run made no progress for 420 s - aborting instead of hanging\n"), os._exit(3)))
-        signal.alarm(420)
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+            "bench.py: multi-rank run made no progress for 300 s - aborting instead of hanging\n"), os._exit(3)))
+        signal.alarm(300)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     _lib.load()
     _lib.set_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.attn_impl])
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -304,66 +360,137 @@ def main():
     for name, a, b in events:
         kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
 
-    # ---- timed region 2: end to end through the public API with pinned-host inputs -> `e2e`
-    def step_e2e():
-        if train:
-            runner.load(host_images, host_labels)          # H2D from pinned memory into the static buffers
-            return runner.run().item()                     # D2H read of the step's loss
-        out_ = infer(host_images.to(dev, non_blocking=True))
-        return float(out_.float().cpu()[0, 0])
+    # ---- timed region 2: end to end through the public API with pinned-host inputs -> `e2e`.
+    # Every step copies its batch H2D from pinned memory and its loss / logits D2H, all inside the timed
+    # region; the copies run on a side stream one batch ahead (runtime.GraphedTrainStep.feed / step_fed)
+    # so they overlap the previous step instead of serialising with it.
+    if train:
+        def e2e_loop(n):
+            runner.feed(host_images, host_labels)
+            last_ = None
+            for i in range(n):
+                if i + 1 < n:
+                    runner.feed(host_images, host_labels)      # batch i+1 travels while step i runs
+                last_ = runner.step_fed()                      # returns the loss of step i-1 (already on the host)
+            return runner.last_loss()                          # the final step's loss: read inside the region
+    else:
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [torch.empty_like(dev_images) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        host_out = torch.zeros(2, batch, mcfg["num_classes"], dtype=torch.float32).pin_memory()
+        out_ev = [torch.cuda.Event() for _ in range(2)]
 
-    for _ in range(2):
-        step_e2e()
+        def feed_inf(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[i & 1])
+                stage[i & 1].copy_(host_images, non_blocking=True)
+                ready[i & 1].record(copy_stream)
+
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream()
+            for ev in free:
+                ev.record(cur)
+            feed_inf(0)
+            for i in range(n):
+                if i + 1 < n:
+                    feed_inf(i + 1)
+                cur.wait_event(ready[i & 1])
+                o = infer(stage[i & 1])
+                free[i & 1].record(cur)
+                if i >= 2:
+                    out_ev[i & 1].synchronize()
+                host_out[i & 1].copy_(o.float(), non_blocking=True)
+                out_ev[i & 1].record(cur)
+            out_ev[(n - 1) & 1].synchronize()
+            return float(host_out[(n - 1) & 1][0, 0])
+
+    e2e_loop(2)
     barrier()
     e0.record()
-    last = None
-    for _ in range(args.steps):
-        last = step_e2e()
+    last = e2e_loop(args.steps)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     h2d = host_images.numel() * host_images.element_size() + host_labels.numel() * host_labels.element_size()
     out = None if train else infer(dev_images)
 
+    def teardown():
+        """Drop the captured graph (it references NCCL work) BEFORE the process group goes: round 1's
+        multi-rank runs had printed their result and then stalled inside destroy_process_group()."""
+        if runner is not None:
+            runner.close()
+        if world > 1:
+            import signal
+            sys.stdout.flush()
+            signal.signal(signal.SIGALRM, lambda *_: os._exit(0))  # result is already printed: never hang at exit
+            signal.alarm(30)
+            torch.cuda.synchronize()
+            dist.barrier()
+            dist.destroy_process_group()
+            signal.alarm(0)
+
     if world > 1:
         import signal
         signal.alarm(0)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown()
         return
 
     peaks = load_peaks()
     value = world * batch * args.steps / (ms_total / 1e3)
     e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
+    # ---- rooflines of the hot-path kernels.  Algorithmic work per launch (SURVEY.md section 8 row M4, DESIGN.md
+    # section 5): attention core fwd 4*N^2*E flop and 8*N*E + 4*H*N bytes (bf16) per image, bwd twice that;
+    # QKV projection 6*N*E^2 flop per image.  `roofline` (the contract key) is the DOMINANT hot-path kernel
+    # (largest share of the step); the others are listed under `rooflines`.
     flops_img, bytes_img = attn_algorithmic(mcfg, tokens)
-    roofline, extra = None, {}
-    if "attn_fwd" in kernel_ms:
-        avg_ms = statistics.mean(kernel_ms["attn_fwd"])
-        flops, byts = flops_img * batch, bytes_img * batch * (1.0 if bf16 else 2.0)
-        tf, gbs = flops / avg_ms / 1e9, byts / avg_ms / 1e6
-        intensity = flops / byts
-        ridge = peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"]
-        if intensity < ridge or not bf16:
-            roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": gbs / peaks["hbm_gbs"], "traffic": None}
-        else:
-            roofline = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None}
-        roofline.update({"kernel": "vrr_attn_fwd", "timed": "CUDA events around every launch, eager re-issue of the same K steps",
-                         "avg_launch_ms": avg_ms, "launches_timed": len(kernel_ms["attn_fwd"]),
-                         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts,
-                         "tflops": tf, "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
-                         "peak_source": peaks["source"] + (" (sustained: kernel timed inside a long step)")})
+    traffic_tab = load_traffic().get(args.workload, {})
+    ridge = peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"]
+    esz = 1.0 if bf16 else 2.0
+    algo = {"attn_fwd": (flops_img * batch, bytes_img * batch * esz),
+            "attn_bwd": (2 * flops_img * batch, 2 * bytes_img * batch * esz)}
+    e_, n_ = mcfg["embed_dim"], tokens
+    algo["qkv_rope_fwd"] = (6.0 * n_ * e_ * e_ * batch, (n_ * e_ + 3 * e_ * e_ / batch + 3 * n_ * e_) * 2.0 * esz * batch)
+    rooflines, extra = {}, {}
     for name, arr in kernel_ms.items():
-        extra[name] = {"avg_launch_ms": statistics.mean(arr), "launches": len(arr)}
-        if name == "attn_bwd":
-            extra[name]["tflops"] = 2 * flops_img * batch / statistics.mean(arr) / 1e9
+        avg_ms = statistics.mean(arr)
+        extra[name] = {"avg_launch_ms": avg_ms, "launches": len(arr), "share_of_step": avg_ms * len(arr) / args.steps / (ms_total / args.steps)}
+        if name not in algo:
+            continue
+        flops, byts = algo[name]
+        tf, gbs = flops / avg_ms / 1e9, byts / avg_ms / 1e6
+        if flops / byts < ridge or not bf16:
+            r = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+        else:
+            r = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                 "frac": tf / peaks["bf16_tflops_sustained"]}
+        r.update({"traffic": traffic_tab.get(name), "kernel": "vrr_" + name,
+                  "timed": "CUDA events around every launch, eager re-issue of the same K steps",
+                  "avg_launch_ms": avg_ms, "launches_timed": len(arr), "algorithmic_flops_per_launch": flops,
+                  "algorithmic_bytes_per_launch": byts, "tflops": tf,
+                  "frac_of_bf16_sustained_peak": tf / peaks["bf16_tflops_sustained"],
+                  "frac_of_bf16_burst_peak": tf / peaks["bf16_tflops"],
+                  "peak_source": peaks["source"] + ": HBM copy bandwidth; bf16 sustained figure (kernel timed inside a long step)",
+                  "traffic_source": traffic_tab.get("_source")})
+        rooflines[name] = r
+    roofline = None
+    if rooflines:
+        dominant = max(rooflines, key=lambda k: extra[k]["share_of_step"])
+        roofline = rooflines[dominant]
     step_tflops = model_flops_per_image(mcfg, tokens, train) * value / 1e12
 
     cpu_baseline = None
+    reference_gpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = cpu_reference_run(wl, steps=3, warmup=1)
+    if world == 1 and not args.no_reference_gpu:
+        if runner is not None:
+            runner.close()
+            runner = None
+        del dp, opt, model
+        torch.cuda.empty_cache()
+        reference_gpu = gpu_reference_run(wl, batch, dev, steps=min(args.steps, 5), warmup=2)
 
     line = {
         "metric": "ViT images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world,
@@ -377,13 +504,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else int(out.numel() * 4)},
         "gpu_launches": int(gpu_launches),
-        "roofline": roofline, "hot_path_kernels": extra, "model_tflops": step_tflops,
+        "roofline": roofline, "rooflines": rooflines, "hot_path_kernels": extra, "model_tflops": step_tflops,
         "mfu_vs_bf16_sustained": step_tflops / peaks["bf16_tflops_sustained"] if bf16 else None,
-        "cpu_baseline": cpu_baseline, "clocks": clocks, "last_result": last,
+        "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu, "clocks": clocks, "last_result": last,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == "__main__":

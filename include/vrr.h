@@ -147,6 +147,12 @@ int vrr_rope_apply(const void* q_in, const void* k_in, const float* cos_tab, con
                    void* q_out, void* k_out, int B, int H, int Nr, int Dh, int rope_mode,
                    int inverse, int dtype, void* stream);
 
+/* Gradient of vrr_rope_apply (inverse == 0) w.r.t. its tables: d_cos, d_sin fp32 with the shape of
+ * cos/sin, written (not accumulated); q_in, k_in = the un-rotated inputs, dq, dk = gradients w.r.t. the
+ * rotated outputs.  Deterministic (no atomics). */
+int vrr_rope_table_grad(const void* q_in, const void* k_in, const void* dq, const void* dk, float* d_cos,
+                        float* d_sin, int B, int H, int Nr, int Dh, int rope_mode, int dtype, void* stream);
+
 /* Plain GEMM used by the backward of the projection: C = op(A) . op(B), row-major operands,
  * op(A) is [M][K] (trans_a: A is stored [K][M]), op(B) is [K][N] (trans_b: B is stored [N][K]).
  * `dtype` is the element type of A and B, `c_dtype` that of C (fp32 C is allowed for bf16 inputs:

@@ -36,7 +36,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, style="dp_zero_grad"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -50,11 +50,25 @@ def _worker(rank, world, port, out):
         x = torch.randn(8, 12, generator=g)
         y = torch.randint(0, 4, (8,), generator=g)
         shard = slice(rank * 4, rank * 4 + 4)
-        for step in range(2):  # second step checks zero_grad / re-arming of the buckets
-            dp.zero_grad()
-            loss = torch.nn.functional.cross_entropy(dp(x[shard]), y[shard])
-            loss.backward()
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)  # lr 0: weights stay put, only the zeroing style matters
+        for step in range(3):  # later steps check zeroing / re-arming of the buckets
+            if style == "dp_zero_grad":
+                dp.zero_grad()
+            else:  # the reference loop (train.py:111): set_to_none=True unbinds every p.grad from its bucket
+                opt.zero_grad()
+            if style == "accumulate":  # two half-shards: the first backward only accumulates locally
+                a, b_ = slice(rank * 4, rank * 4 + 2), slice(rank * 4 + 2, rank * 4 + 4)
+                with dp.no_sync():
+                    (torch.nn.functional.cross_entropy(dp(x[a]), y[a]) * 0.5).backward()
+                (torch.nn.functional.cross_entropy(dp(x[b_]), y[b_]) * 0.5).backward()
+            else:
+                loss = torch.nn.functional.cross_entropy(dp(x[shard]), y[shard])
+                loss.backward()
             dp.sync()
+            opt.step()
+        for b in dp.buckets:  # whatever the zeroing style, the gradients live in the flat buckets again
+            for p in b.params:
+                assert p.grad.data_ptr() == b.views[id(p)].data_ptr()
         for p in net.parameters():
             assert p.grad is not None and p.grad.data_ptr() != 0
         out[rank] = ({k: v.detach().clone() for k, v in net.state_dict().items()},
@@ -63,12 +77,13 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_bucketed_dp_matches_single_process():
+@pytest.mark.parametrize("style", ["dp_zero_grad", "optimizer_zero_grad", "accumulate"])
+def test_bucketed_dp_matches_single_process(style):
     world = 2
     port = _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, style), nprocs=world, join=True)
     (sd0, g0), (sd1, g1) = out[0], out[1]
     for k in sd0:  # broadcast from rank 0 at construction
         assert torch.equal(sd0[k], sd1[k]), k
@@ -98,3 +113,25 @@ def test_single_process_wrapper_is_transparent():
         assert torch.allclose(p.grad, q.grad, atol=1e-6), n
     with pytest.raises(ValueError):
         BucketedDataParallel(torch.nn.ReLU())
+
+
+def test_single_process_optimizer_zero_grad_rebinds():
+    """optimizer.zero_grad() (set_to_none=True) between steps: gradients are re-bound to the buckets and
+    match a plain module, step after step."""
+    net = TinyNet()
+    ref = TinyNet()
+    ref.load_state_dict(net.state_dict())
+    dp = BucketedDataParallel(net, bucket_mb=0.001)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for step in range(3):
+        x = torch.randn(4, 12, generator=torch.Generator().manual_seed(step))
+        opt.zero_grad()
+        ropt.zero_grad()
+        dp(x).sum().backward()
+        dp.sync()
+        ref(x).sum().backward()
+        for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), (step, n)
+        opt.step()
+        ropt.step()

@@ -560,6 +560,26 @@ def test_apply_rotary_emb_public_function(rope):
     ones = np.ones((b, h, n, d))
     assert err_scaled(qd.grad, A.rotate_half_inverse(ones, c, s)) <= FP32_TOL
     assert err_scaled(kd.grad, 2 * A.rotate_half_inverse(ones, c, s)) <= FP32_TOL
+    # the tables are differentiable too (the reference's rope_utils is plain torch arithmetic): autograd of
+    # the same expression in float64
+    cr, sr = cos.double().requires_grad_(True), sin.double().requires_grad_(True)
+    qr, kr = q.double(), k.double()
+    cb = cr if rope == "mixed" else cr[None]
+    sb = sr if rope == "mixed" else sr[None]
+    h2 = d // 2
+
+    def rot(x):
+        return torch.cat([x[..., :h2] * cb - x[..., h2:] * sb, x[..., :h2] * sb + x[..., h2:] * cb], dim=-1)
+
+    wq, wk = torch.randn(b, h, n, d, generator=g).double(), torch.randn(b, h, n, d, generator=g).double()
+    ((rot(qr) * wq).sum() + (rot(kr) * wk).sum()).backward()
+    cd, sd_ = cos.to(DEV).requires_grad_(True), sin.to(DEV).requires_grad_(True)
+    qo2, ko2 = models.apply_rotary_emb(q.to(DEV), k.to(DEV), models.reshape_for_broadcast(cd, tgt),
+                                       models.reshape_for_broadcast(sd_, tgt))
+    ((qo2 * wq.float().to(DEV)).sum() + (ko2 * wk.float().to(DEV)).sum()).backward()
+    assert cd.grad is not None and cd.grad.shape == cos.shape
+    check_fp32(cd.grad, cr.grad, f"apply_rotary_emb {rope} d_cos")
+    check_fp32(sd_.grad, sr.grad, f"apply_rotary_emb {rope} d_sin")
 
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])

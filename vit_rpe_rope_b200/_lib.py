@@ -46,6 +46,7 @@ SIGNATURES = {
     "vrr_qkv_rope_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "vrr_qkv_rope_bwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
     "vrr_rope_apply": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
+    "vrr_rope_table_grad": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "vrr_gemm": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "vrr_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "vrr_layernorm_bwd": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_void_p]),

@@ -76,4 +76,7 @@ int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab,
 int rope_apply(const void* q_in, const void* k_in, const float* cos_tab, const float* sin_tab, void* q_out,
                void* k_out, int B, int H, int Nr, int Dh, int rope_mode, int inverse, int dtype, cudaStream_t st);
 
+int rope_table_grad(const void* q_in, const void* k_in, const void* dq, const void* dk, float* d_cos, float* d_sin,
+                    int B, int H, int Nr, int Dh, int rope_mode, int dtype, cudaStream_t st);
+
 }  // namespace vrr

@@ -177,4 +177,47 @@ int rope_apply(const void* q_in, const void* k_in, const float* cos_tab, const f
   return VRR_OK;
 }
 
+// Gradient of the stand-alone rotate-half w.r.t. its tables: d_cos = sum (g1 x1 + g2 x2),
+// d_sin = sum (g2 x1 - g1 x2) over q and k, over the batch (and over heads for the head-shared axial
+// table).  One thread per table entry, a plain loop over what it sums: deterministic, no atomics.
+template <typename T>
+__global__ void rope_table_grad_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in,
+                                       const T* __restrict__ dq, const T* __restrict__ dk, float* __restrict__ d_cos,
+                                       float* __restrict__ d_sin, int B, int H, int Nr, int Dh, int rope_mode) {
+  const int hd = Dh >> 1;
+  const int heads_tab = rope_mode == VRR_ROPE_MIXED ? H : 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= heads_tab * Nr * hd) return;
+  const int dd = idx % hd, t = (idx / hd) % Nr, ht = idx / (hd * Nr);
+  const int h0 = rope_mode == VRR_ROPE_MIXED ? ht : 0, h1 = rope_mode == VRR_ROPE_MIXED ? ht + 1 : H;
+  float ac = 0.f, as = 0.f;
+  for (int b = 0; b < B; ++b)
+    for (int h = h0; h < h1; ++h) {
+      const size_t o = (((size_t)b * H + h) * Nr + t) * Dh + dd;
+      const float q1 = Elem<T>::ld(q_in + o), q2 = Elem<T>::ld(q_in + o + hd);
+      const float k1 = Elem<T>::ld(k_in + o), k2 = Elem<T>::ld(k_in + o + hd);
+      const float gq1 = Elem<T>::ld(dq + o), gq2 = Elem<T>::ld(dq + o + hd);
+      const float gk1 = Elem<T>::ld(dk + o), gk2 = Elem<T>::ld(dk + o + hd);
+      ac += gq1 * q1 + gq2 * q2 + gk1 * k1 + gk2 * k2;
+      as += gq2 * q1 - gq1 * q2 + gk2 * k1 - gk1 * k2;
+    }
+  d_cos[idx] = ac;
+  d_sin[idx] = as;
+}
+
+int rope_table_grad(const void* q_in, const void* k_in, const void* dq, const void* dk, float* d_cos, float* d_sin,
+                    int B, int H, int Nr, int Dh, int rope_mode, int dtype, cudaStream_t st) {
+  const int total = (rope_mode == VRR_ROPE_MIXED ? H : 1) * Nr * (Dh / 2);
+  const int threads = 128, blocks = ceil_div(total, threads);
+  if (dtype == VRR_F32)
+    rope_table_grad_kernel<float><<<blocks, threads, 0, st>>>((const float*)q_in, (const float*)k_in, (const float*)dq,
+                                                             (const float*)dk, d_cos, d_sin, B, H, Nr, Dh, rope_mode);
+  else
+    rope_table_grad_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(
+        (const __nv_bfloat16*)q_in, (const __nv_bfloat16*)k_in, (const __nv_bfloat16*)dq, (const __nv_bfloat16*)dk,
+        d_cos, d_sin, B, H, Nr, Dh, rope_mode);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
 }  // namespace vrr

@@ -239,6 +239,17 @@ int vrr_rope_apply(const void* q_in, const void* k_in, const float* cos_tab, con
                     (cudaStream_t)stream);
 }
 
+int vrr_rope_table_grad(const void* q_in, const void* k_in, const void* dq, const void* dk, float* d_cos,
+                        float* d_sin, int B, int H, int Nr, int Dh, int rope_mode, int dtype, void* stream) {
+  VRR_REQUIRE(q_in && k_in && dq && dk && d_cos && d_sin, VRR_ERR_INVALID_ARG, "rope_table_grad: NULL pointer");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "rope_table_grad: bad dtype %d", dtype);
+  VRR_REQUIRE(rope_mode == VRR_ROPE_AXIAL || rope_mode == VRR_ROPE_MIXED, VRR_ERR_INVALID_ARG,
+              "rope_table_grad: bad rope_mode %d", rope_mode);
+  VRR_REQUIRE(B > 0 && H > 0 && Nr > 0 && Dh > 0 && Dh % 2 == 0, VRR_ERR_INVALID_ARG, "rope_table_grad: bad sizes");
+  if (int rc = require_device()) return rc;
+  return rope_table_grad(q_in, k_in, dq, dk, d_cos, d_sin, B, H, Nr, Dh, rope_mode, dtype, (cudaStream_t)stream);
+}
+
 int vrr_gemm(const void* a, const void* b, void* c, int M, int N, int K, int trans_a, int trans_b, int dtype,
              int c_dtype, void* stream) {
   VRR_REQUIRE(a && b && c, VRR_ERR_INVALID_ARG, "gemm: NULL pointer");

@@ -2,7 +2,7 @@
 gradients all-reduced in flat buckets that overlap with the rest of backward.
 
 The reference has no multi-GPU code; images are independent units, so forward/backward need no
-exchange and the single collective is the gradient sum before ``optimizer.step``.  Design:
+exchange and the single collective is the gradient mean before ``optimizer.step``.  Design:
 
 * parameters are grouped into flat fp32 buckets (~``bucket_mb`` each) in *reverse registration
   order* - the order backward produces their gradients; parameters whose gradient only completes
@@ -10,13 +10,22 @@ exchange and the single collective is the gradient sum before ``optimizer.step``
   the patch projection, an absolute table) go into the last bucket;
 * ``param.grad`` is a view into its bucket, so the weight-gradient kernels accumulate straight
   into bucket memory - no gather copy before the collective;
-* a post-accumulate hook counts a bucket's gradients; when the last one lands the bucket is
-  pre-scaled by 1/world and all-reduced asynchronously (NCCL runs it on its own stream, behind an
-  event on the compute stream), while backward keeps computing earlier layers;
-* ``sync()`` (called before the optimizer step) makes the compute stream wait for the collectives.
+* a post-accumulate hook marks a parameter as seen for this step; when the last parameter of a
+  bucket has been seen the bucket is all-reduced asynchronously with ``ReduceOp.AVG`` (NCCL runs it
+  on its own stream, behind an event on the compute stream) while backward keeps computing earlier
+  layers.  Backends without AVG (gloo, the CPU tests) pre-scale by 1/world and SUM;
+* ``sync()`` (called before the optimizer step) makes the compute stream wait for the collectives
+  and re-arms the buckets for the next step.
+
+Works with either zeroing style: ``dp.zero_grad()`` (zeroes the flat buckets in place, cheapest) or
+the reference loop's ``optimizer.zero_grad()`` (train.py:111; ``set_to_none=True`` unbinds every
+``p.grad``): the hook notices a gradient that no longer aliases its bucket slice, copies it in and
+re-binds ``p.grad`` to the slice.  Gradient accumulation over several backwards: wrap all but the
+last one in ``with dp.no_sync():``.
 
 Works unchanged on CPU tensors with the ``gloo`` backend (tests/test_dp_gloo.py, world_size 2).
 """
+import contextlib
 from typing import List
 
 import torch
@@ -28,11 +37,15 @@ class _Bucket:
         self.params = params
         self.numel = sum(p.numel() for p in params)
         self.flat = torch.zeros(self.numel, device=device, dtype=dtype)
-        self.pending = len(params)
+        self.views = {}
+        self.seen = set()
         self.work = None
+        self.reduced = False
         off = 0
         for p in params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            v = self.flat[off:off + p.numel()].view_as(p)
+            self.views[id(p)] = v
+            p.grad = v
             off += p.numel()
 
 
@@ -43,6 +56,9 @@ class BucketedDataParallel(torch.nn.Module):
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        backend = dist.get_backend(process_group) if dist.is_initialized() else ""
+        self._use_avg = str(backend).lower() == "nccl"
+        self._sync_enabled = True
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise ValueError("module has no trainable parameters")
@@ -87,25 +103,72 @@ class BucketedDataParallel(torch.nn.Module):
 
     def _on_grad(self, p):
         b = self._bucket_of[id(p)]
-        b.pending -= 1
-        if b.pending == 0 and self.world > 1:
+        view = b.views[id(p)]
+        g = p.grad
+        if g is not None and (g.data_ptr() != view.data_ptr() or g.dtype != view.dtype):
+            # the caller unbound p.grad (optimizer.zero_grad(set_to_none=True)): autograd produced a
+            # fresh tensor - move it into the bucket and bind the parameter to its slice again
+            if b.reduced:
+                raise RuntimeError("a gradient arrived for a bucket that was already all-reduced in this step; "
+                                   "wrap all but the last backward of an accumulation step in dp.no_sync()")
+            view.copy_(g)
+            p.grad = view
+        if b.reduced:
+            raise RuntimeError("a gradient arrived for a bucket that was already all-reduced in this step; "
+                               "wrap all but the last backward of an accumulation step in dp.no_sync()")
+        if not self._sync_enabled:
+            return
+        b.seen.add(id(p))
+        if len(b.seen) == len(b.params):
+            self._launch(b)
+
+    def _launch(self, b):
+        b.reduced = True
+        if self.world <= 1:
+            return
+        if self._use_avg:
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
             b.flat.mul_(1.0 / self.world)
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Backwards inside this context only accumulate locally (gradient accumulation)."""
+        prev, self._sync_enabled = self._sync_enabled, False
+        try:
+            yield
+        finally:
+            self._sync_enabled = prev
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
-    def zero_grad(self, set_to_none: bool = False):  # noqa: ARG002 - grads must stay views of the buckets
+    def zero_grad(self, set_to_none: bool = False):  # noqa: ARG002 - grads stay views of the buckets
         for b in self.buckets:
             b.flat.zero_()
-            b.pending = len(b.params)
-            b.work = None
+            for p in b.params:
+                if p.grad is None or p.grad.data_ptr() != b.views[id(p)].data_ptr():
+                    p.grad = b.views[id(p)]
+            self._rearm(b)
+
+    @staticmethod
+    def _rearm(b):
+        b.seen.clear()
+        b.work = None
+        b.reduced = False
 
     def sync(self):
-        """Wait for every bucket's all-reduce (call after ``backward``, before ``optimizer.step``)."""
+        """Wait for every bucket's all-reduce (call after ``backward``, before ``optimizer.step``) and
+        re-arm the buckets for the next step."""
+        missing = [b for b in self.buckets if not b.reduced]
+        if missing and self.world > 1:
+            names = {id(p): n for n, p in self.module.named_parameters()}
+            absent = [names.get(id(p), "?") for b in missing for p in b.params if id(p) not in b.seen]
+            raise RuntimeError(f"{len(missing)} gradient bucket(s) were never all-reduced: no gradient reached "
+                               f"{absent[:6]}{'...' if len(absent) > 6 else ''} in this step (unused parameter, or "
+                               "every backward of the step ran under no_sync())")
         for b in self.buckets:
-            if b.pending != 0 and self.world > 1:
-                raise RuntimeError("a bucket never completed: some parameter received no gradient")
             if b.work is not None:
                 b.work.wait()
-                b.work = None
+            self._rearm(b)

@@ -106,6 +106,8 @@ class PatchEmbedFn(torch.autograd.Function):
             _lib.check(lib.vrr_patch_embed_fwd(_ptr(images), _ptr(w), _ptr(b), _ptr(cls), _ptr(pos), _ptr(tokens),
                                                _ptr(ws), ws_bytes, B, C, Hi, Wi, patch, E, _DT[idt], _DT[dt],
                                                _DT[tdt], _stream()), "vrr_patch_embed_fwd")
+        if ctx.needs_input_grad[0]:
+            ctx.w_for_dimg = w
         ctx.save_for_backward(images)
         ctx.meta = (B, C, Hi, Wi, patch, E, Np, pos_embed.shape if pos_embed is not None else None,
                     weight.shape, cls_token.shape, idt, dt, tdt)
@@ -537,18 +539,28 @@ class RopeApplyFn(torch.autograd.Function):
         with torch.cuda.device(q.device):
             _lib.check(lib.vrr_rope_apply(_ptr(q), _ptr(k), _ptr(c32), _ptr(s32), _ptr(qo), _ptr(ko), B, H, Nr, Dh,
                                           mode, 0, _DT[q.dtype], _stream()), "vrr_rope_apply")
-        ctx.save_for_backward(c32, s32)
-        ctx.meta = (B, H, Nr, Dh, mode)
+        need_tab = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        ctx.save_for_backward(c32, s32, *((q, k) if need_tab else ()))
+        ctx.meta = (B, H, Nr, Dh, mode, cos.shape, sin.shape, cos.dtype, sin.dtype)
         return qo, ko
 
     @staticmethod
     def backward(ctx, dq, dk):
         lib = _lib.load()
-        c32, s32 = ctx.saved_tensors
-        B, H, Nr, Dh, mode = ctx.meta
+        c32, s32 = ctx.saved_tensors[:2]
+        B, H, Nr, Dh, mode, cos_shape, sin_shape, cos_dt, sin_dt = ctx.meta
         dq, dk = dq.contiguous(), dk.contiguous()
         gq, gk = torch.empty_like(dq), torch.empty_like(dk)
+        d_cos = d_sin = None
         with torch.cuda.device(dq.device):
             _lib.check(lib.vrr_rope_apply(_ptr(dq), _ptr(dk), _ptr(c32), _ptr(s32), _ptr(gq), _ptr(gk), B, H, Nr,
                                           Dh, mode, 1, _DT[dq.dtype], _stream()), "vrr_rope_apply")
-        return gq, gk, None, None
+            if len(ctx.saved_tensors) == 4:  # the tables are differentiable too (RoPEMixed.freqs feeds them)
+                q, k = ctx.saved_tensors[2:]
+                d_cos, d_sin = torch.empty_like(c32), torch.empty_like(s32)
+                _lib.check(lib.vrr_rope_table_grad(_ptr(q), _ptr(k), _ptr(dq), _ptr(dk), _ptr(d_cos), _ptr(d_sin), B, H,
+                                                   Nr, Dh, mode, _DT[dq.dtype], _stream()), "vrr_rope_table_grad")
+                # undo the broadcast of reshape_for_broadcast: sum_to_size restores [1, 1|H, Nr, Dh/2] / the raw shape
+                d_cos = d_cos.reshape((1,) * (len(cos_shape) - d_cos.ndim) + tuple(d_cos.shape)).sum_to_size(cos_shape).to(cos_dt)
+                d_sin = d_sin.reshape((1,) * (len(sin_shape) - d_sin.ndim) + tuple(d_sin.shape)).sum_to_size(sin_shape).to(sin_dt)
+        return gq, gk, (d_cos if ctx.needs_input_grad[2] else None), (d_sin if ctx.needs_input_grad[3] else None)
