@@ -7,9 +7,8 @@ gradients max-abs <= 1e-5 in fp32 and <= 2e-2 relative in bf16.
   up only for tensors whose own magnitude exceeds 1), AND - because most gradients are far below 1 in
   magnitude, where an absolute bar alone is weak - ``err_rel`` = max|a-b| / max|b| must be <=
   FP32_REL_TOL (summation-order noise of fp32 reductions over 1e3..1e5 terms stays well inside it).
-* bf16: ``err_rel`` <= 2e-2, flat, against the fp32 oracle.  One documented exception class: a tensor
-  for which the REFERENCE's own autocast run is already further than 1e-2 from the fp32 oracle
-  (bf16 rounding noise dominates a small-magnitude gradient) is held to 2x the reference's own error.
+* bf16: ``err_rel`` <= 2e-2, flat, against the fp32 oracle, for logits and every gradient tensor (the
+  reference's own autocast run is measured beside it and reported, but buys no allowance).
 * every bf16 head-dim-64 case asserts that the tcgen05 kernel family ran (``vrr_family_count``).
 
 Observed worst errors are appended to ``gpurun_out/parity_report.txt`` (when that directory exists).
@@ -34,7 +33,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 MODES = ("none", "absolute", "relative", "polynomial", "rope-axial", "rope-mixed")
 MODEL_TAGS = ["none", "absolute", "relative", "polynomial", "polynomial_perhead", "rope_axial", "rope_mixed"]
 FP32_TOL = 1e-5
-FP32_REL_TOL = 2e-4
+FP32_REL_TOL = 5e-5
 BF16_TOL = 2e-2
 DEV = "cuda:0"
 _REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.txt")
@@ -70,7 +69,7 @@ def check_fp32(got, want, what=""):
 def check_bf16(got, want32, ref16=None, what=""):
     e_mine = err_rel(got, want32)
     e_ref = err_rel(ref16, want32) if ref16 is not None else 0.0
-    bound = BF16_TOL if e_ref <= BF16_TOL / 2 else 2 * e_ref
+    bound = BF16_TOL
     report(f"bf16 {what}: mine {e_mine:.2e} ref-autocast {e_ref:.2e} bound {bound:.2e}")
     assert e_mine <= bound, (what, e_mine, e_ref)
 

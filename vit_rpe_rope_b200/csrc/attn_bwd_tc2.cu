@@ -571,7 +571,8 @@ bool attn_bwd_tc2_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bi
   if ((long long)3 * B * H * N >= (1ll << 31)) return false;
   const int mode = bias ? bias->mode : VRR_BIAS_NONE;
   if (mode == VRR_BIAS_POLY && (bias->grid > 255 || bias->len > 4)) return false;
-  return bwd2_smem_bytes(N, bias, nullptr, false) <= 110 * 1024 && bwd2_smem_bytes(N, bias, nullptr, true) <= 110 * 1024;
+  // up to 113 KB keeps two CTAs per SM; the relative table at >= ~900 tokens needs more and runs one CTA per SM
+  return bwd2_smem_bytes(N, bias, nullptr, false) <= 200 * 1024 && bwd2_smem_bytes(N, bias, nullptr, true) <= 200 * 1024;
 }
 
 int attn_bwd_tc2(const void* planes, const vrr_bias_desc* bias, const void* out, const void* d_out, const float* lse,
@@ -607,8 +608,8 @@ int attn_bwd_tc2(const void* planes, const vrr_bias_desc* bias, const void* out,
   const size_t smem_kv = bwd2_smem_bytes(N, bias, &p.lut_floats, true);
 #define LAUNCH(MODE)                                                                                             \
   do {                                                                                                           \
-    VRR_SMEM_ATTR_ONCE(attn_bwd_dq_tc2_kernel<MODE>, 110 * 1024);                                                \
-    VRR_SMEM_ATTR_ONCE(attn_bwd_dkv_tc2_kernel<MODE>, 110 * 1024);                                               \
+    VRR_SMEM_ATTR_ONCE(attn_bwd_dq_tc2_kernel<MODE>, 200 * 1024);                                                \
+    VRR_SMEM_ATTR_ONCE(attn_bwd_dkv_tc2_kernel<MODE>, 200 * 1024);                                               \
     attn_bwd_dq_tc2_kernel<MODE><<<grid, kThreads, smem_q, st>>>(tm_pl, tm_do, p);                               \
     VRR_LAUNCHED();                                                                                              \
     attn_bwd_dkv_tc2_kernel<MODE><<<grid, kThreads, smem_kv, st>>>(tm_pl, tm_do, p);                             \
