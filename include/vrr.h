@@ -69,6 +69,9 @@ typedef enum { VRR_BIAS_NONE = 0, VRR_BIAS_TABLE = 1, VRR_BIAS_POLY = 2 } vrr_bi
  * tcgen05 has no fp32 MMA and the fp32 parity bar is 1e-5. */
 typedef enum { VRR_IMPL_AUTO = 0, VRR_IMPL_SIMT = 1, VRR_IMPL_TCGEN05 = 2 } vrr_impl;
 
+/* Epilogues of vrr_gemm_ex (Linear layers, models/vit.py:91,118,285). */
+typedef enum { VRR_EPI_NONE = 0, VRR_EPI_BIAS = 1, VRR_EPI_BIAS_GELU = 2 } vrr_epilogue;
+
 typedef struct {
   int32_t mode;        /* vrr_bias_mode                                                  */
   int32_t heads;       /* rows of `param`: H for TABLE; 1 or H for POLY                  */
@@ -90,7 +93,8 @@ uint64_t vrr_launch_count(void);
  * VRR_IMPL_AUTO instead of trusting the selection silently. */
 uint64_t vrr_family_count(int family);
 /* Tuning / experiment switches (process-wide): "attn_fwd_table_bulk" (0/1),
- * "attn_fwd_rescale_threshold_x100". */
+ * "attn_fwd_rescale_threshold_x100", "gemm_variant" (2 = CTA-pair kernels, default; 1 = 1-CTA kernels for the
+ * QKV / patch-embed GEMMs, kept for A/B measurements). */
 int vrr_set_option(const char* name, int value);
 /* Debug: one CTA of the next attention-forward launches records clock64() phase stamps (8 per key
  * tile, first 8 tiles) into `device_buf` (64 x int64); NULL switches it off. */
@@ -159,6 +163,21 @@ int vrr_rope_table_grad(const void* q_in, const void* k_in, const void* dq, cons
  * weight gradients).  fp32 accumulation always. */
 int vrr_gemm(const void* a, const void* b, void* c, int M, int N, int K, int trans_a, int trans_b,
              int dtype, int c_dtype, void* stream);
+
+/* GEMM of the Linear layers of the path and of their backward, with fused epilogues:
+ * C[M][N] = op(A).op(B) with the vrr_gemm operand conventions; `dtype` = element type of A and B.
+ *   forward  y = x.W^T (+b)        : trans_a 0, trans_b 1   (models/vit.py:47,91,118,285)
+ *   backward dX = dY.W             : trans_a 0, trans_b 0
+ *   backward dW = dY^T.X           : trans_a 1, trans_b 0, c_dtype VRR_F32
+ * epilogue (vrr_epilogue): BIAS adds the fp32 `bias[N]` (cast to `dtype` first, like F.linear on `dtype`
+ * tensors) before the single rounding to c_dtype; BIAS_GELU additionally writes C2 = gelu(C), exact erf GELU
+ * (timm Mlp, act_layer=nn.GELU).  accumulate != 0 (fp32 C, tcgen05 kernel only): C += result.
+ * bf16 operands with N % 8 == 0, K % 8 == 0 (and M % 8 == 0 when trans_a) and 16-byte aligned pointers run
+ * the tcgen05 CTA-pair kernel (cta_group::2, TMA in, TMA store / reduce-add out; fp32 C is split over K and
+ * combined by TMA reduce-add, so its summation order is not deterministic); everything else (fp32 operands,
+ * odd shapes) runs the FFMA kernel.  vrr_set_impl() forces a family; vrr_family_count() reports it. */
+int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K,
+                int trans_a, int trans_b, int dtype, int c_dtype, int epilogue, int accumulate, void* stream);
 
 /* ---- (b) fused attention: models/vit.py:71-88 ---------------------------------------------- */
 /* out = merge_heads(softmax(q k^T * scale + bias) v), lse = log-sum-exp of the logits.

@@ -1,0 +1,19 @@
+"""Run one GEMM shape through vrr_gemm_ex a few times (for ncu): python scripts/gemm_one.py M N K ta tb [f32]"""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vit_rpe_rope_b200 import _lib
+lib = _lib.load()
+M, N, K, ta, tb = (int(v) for v in sys.argv[1:6])
+f32 = len(sys.argv) > 6 and sys.argv[6] == "f32"
+dev = "cuda:0"
+a = torch.randn((K, M) if ta else (M, K)).to(torch.bfloat16).to(dev)
+b = torch.randn((N, K) if tb else (K, N)).to(torch.bfloat16).to(dev)
+c = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+p = lambda t: ctypes.c_void_p(t.data_ptr())
+for _ in range(5):
+    rc = lib.vrr_gemm_ex(p(a), p(b), p(c), None, None, M, N, K, ta, tb, 1, 0 if f32 else 1, 0, 0, st)
+    assert rc == 0, _lib.last_error()
+torch.cuda.synchronize()
+print("ok", c.float().abs().mean().item())

@@ -17,6 +17,7 @@ VRR_F32, VRR_BF16 = 0, 1
 ROPE_NONE, ROPE_AXIAL, ROPE_MIXED = 0, 1, 2
 BIAS_NONE, BIAS_TABLE, BIAS_POLY = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU = 0, 1, 2
 
 STATUS_NAMES = {0: "VRR_OK", -1: "VRR_ERR_INVALID_ARG", -2: "VRR_ERR_UNSUPPORTED",
                 -3: "VRR_ERR_NO_DEVICE", -4: "VRR_ERR_CUDA", -5: "VRR_ERR_WORKSPACE"}
@@ -48,6 +49,7 @@ SIGNATURES = {
     "vrr_rope_apply": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "vrr_rope_table_grad": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "vrr_gemm": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    "vrr_gemm_ex": (c_int, [c_void_p] * 5 + [c_int] * 9 + [c_void_p]),
     "vrr_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "vrr_layernorm_bwd": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_void_p]),
     "vrr_add_layernorm_fwd": (c_int, [c_void_p] * 8 + [c_int, c_int, c_float, c_int, c_int, c_void_p]),

@@ -67,6 +67,27 @@ struct StoreEpilogue {
     Elem<T>::st(c + (long long)m * ldc + n, v);
   }
 };
+// Linear-layer epilogue: c = round_T(acc + bias[n]) (bias cast to T first, like F.linear on T tensors);
+// optionally c2 = gelu(c) with the exact erf GELU.
+template <typename T>
+struct BiasEpilogue {
+  T* c;
+  T* c2;
+  const float* bias;
+  long long ldc;
+  int gelu;
+  __device__ __forceinline__ void operator()(int m, int n, float v, const float*, int) const {
+    float b = bias[n];
+    if (sizeof(T) == 2) b = __bfloat162float(__float2bfloat16_rn(b));
+    T r;
+    Elem<T>::st(&r, v + b);
+    c[(long long)m * ldc + n] = r;
+    if (gelu) {
+      const float h = Elem<T>::ld(&r);
+      Elem<T>::st(c2 + (long long)m * ldc + n, 0.5f * h * (1.f + erff(h * 0.70710678118654752f)));
+    }
+  }
+};
 struct AtomicEpilogue {  // split-K accumulation into a zeroed fp32 C
   float* c;
   long long ldc;
@@ -229,6 +250,24 @@ static int gemm_t(const void* a, const void* b, void* c, int M, int N, int K, in
   GO(false, false);
 #undef GO
 }
+template <typename T>
+static int gemm_bias_t(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int ta,
+                       int tb, int gelu, cudaStream_t st) {
+  StridedOperand<T> A = ta ? StridedOperand<T>{(const T*)a, 1, M} : StridedOperand<T>{(const T*)a, K, 1};
+  StridedOperand<T> Bo = tb ? StridedOperand<T>{(const T*)b, K, 1} : StridedOperand<T>{(const T*)b, 1, N};
+  BiasEpilogue<T> epi{(T*)c, (T*)c2, bias, N, gelu};
+  if (!ta && tb) return launch_gemm<StridedOperand<T>, StridedOperand<T>, BiasEpilogue<T>, true, true>(A, Bo, epi, M, N, K, 1, st);
+  if (!ta && !tb) return launch_gemm<StridedOperand<T>, StridedOperand<T>, BiasEpilogue<T>, true, false>(A, Bo, epi, M, N, K, 1, st);
+  if (ta && tb) return launch_gemm<StridedOperand<T>, StridedOperand<T>, BiasEpilogue<T>, false, true>(A, Bo, epi, M, N, K, 1, st);
+  return launch_gemm<StridedOperand<T>, StridedOperand<T>, BiasEpilogue<T>, false, false>(A, Bo, epi, M, N, K, 1, st);
+}
+// C = round(op(A).op(B) + bias) (+ C2 = gelu(C)); C has the operands' element type.
+int gemm_simt_bias(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int ta, int tb,
+                   int dtype, int gelu, cudaStream_t st) {
+  if (dtype == VRR_F32) return gemm_bias_t<float>(a, b, c, c2, bias, M, N, K, ta, tb, gelu, st);
+  return gemm_bias_t<__nv_bfloat16>(a, b, c, c2, bias, M, N, K, ta, tb, gelu, st);
+}
+
 int gemm_simt(const void* a, const void* b, void* c, int M, int N, int K, int ta, int tb, int dtype,
               int c_dtype, cudaStream_t st) {
   if (dtype == VRR_F32 && c_dtype == VRR_F32) return gemm_t<float, float>(a, b, c, M, N, K, ta, tb, st);

@@ -32,6 +32,8 @@ int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const 
                       int B, int N, int E, int H, int rope_mode, int dtype, cudaStream_t st);
 int gemm_simt(const void* a, const void* b, void* c, int M, int N, int K, int ta, int tb, int dtype,
               int c_dtype, cudaStream_t st);
+int gemm_simt_bias(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int ta, int tb,
+                   int dtype, int gelu, cudaStream_t st);
 int patch_embed_fwd_simt(const void* images, const void* weight, const void* bias, const void* cls,
                          const void* pos, void* tokens, int B, int C, int Hi, int Wi, int P, int E, int img_dtype,
                          int dtype, int tok_dtype, cudaStream_t st);
@@ -51,6 +53,17 @@ int patch_unfold(const void* images, void* out, int B, int C, int Hi, int Wi, in
 int patch_embed_fwd_tc(const void* images, const void* weight, const void* bias, const void* pos, void* tokens,
                        void* workspace, int B, int C, int Hi, int Wi, int P, int E, int img_dtype, int tok_dtype,
                        cudaStream_t st);
+
+// gemm_tc2.cu (tcgen05 CTA pairs, cta_group::2: every operand layout, TMA-store epilogues)
+void gemm_tc_set_variant(int v);  // 2 (default): CTA-pair kernels; 1: the 1-CTA kernels of gemm_tc.cu (QKV / patch embed only)
+int gemm_tc_variant();
+bool gemm_bf16_tc_supported(int M, int N, int K, int trans_a, int trans_b, int c_dtype, int epilogue);
+int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int trans_a,
+                 int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st);
+int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes, int B, int N,
+                     int E, int H, int rope_mode, cudaStream_t st);
+int patch_embed_gemm_tc2(const void* unfolded, const void* weight, const void* bias, const void* pos, void* tokens, int M,
+                         int Np, int K, int E, int tok_dtype, cudaStream_t st);
 
 // layernorm.cu
 int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int E,

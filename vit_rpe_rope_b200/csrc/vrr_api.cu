@@ -126,6 +126,7 @@ int vrr_debug_timestamps(void* device_buf) {  /* 64 x int64 device buffer, or NU
 }
 int vrr_set_option(const char* name, int value) {
   if (!name) return VRR_ERR_INVALID_ARG;
+  if (!strcmp(name, "gemm_variant")) { gemm_tc_set_variant(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_rescale_threshold_x100")) { attn_fwd_tc_set_threshold_x100(value); return VRR_OK; }
   set_error("vrr_set_option: unknown option '%s'", name);
@@ -200,6 +201,8 @@ int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, con
   const int impl = g_impl.load();
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && qkv_rope_fwd_tc_supported(B, N, E, H)) {
     VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
+    if (gemm_tc_variant() == 2)
+      return qkv_rope_fwd_tc2(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
     return qkv_rope_fwd_tc(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
   }
   VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
@@ -256,6 +259,33 @@ int vrr_gemm(const void* a, const void* b, void* c, int M, int N, int K, int tra
   VRR_REQUIRE(M > 0 && N > 0 && K > 0, VRR_ERR_INVALID_ARG, "gemm: bad sizes");
   VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(c_dtype), VRR_ERR_INVALID_ARG, "gemm: bad dtype %d/%d", dtype, c_dtype);
   if (int rc = require_device()) return rc;
+  return gemm_simt(a, b, c, M, N, K, trans_a, trans_b, dtype, c_dtype, (cudaStream_t)stream);
+}
+
+int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int trans_a,
+                int trans_b, int dtype, int c_dtype, int epilogue, int accumulate, void* stream) {
+  VRR_REQUIRE(a && b && c, VRR_ERR_INVALID_ARG, "gemm_ex: NULL pointer");
+  VRR_REQUIRE(M > 0 && N > 0 && K > 0, VRR_ERR_INVALID_ARG, "gemm_ex: bad sizes");
+  VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(c_dtype), VRR_ERR_INVALID_ARG, "gemm_ex: bad dtype %d/%d", dtype, c_dtype);
+  VRR_REQUIRE(epilogue >= VRR_EPI_NONE && epilogue <= VRR_EPI_BIAS_GELU, VRR_ERR_INVALID_ARG, "gemm_ex: bad epilogue %d", epilogue);
+  VRR_REQUIRE(epilogue == VRR_EPI_NONE || bias, VRR_ERR_INVALID_ARG, "gemm_ex: the bias epilogues need `bias`");
+  VRR_REQUIRE(epilogue != VRR_EPI_BIAS_GELU || c2, VRR_ERR_INVALID_ARG, "gemm_ex: BIAS_GELU needs `c2`");
+  if (int rc = require_device()) return rc;
+  const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && gemm_bf16_tc_supported(M, N, K, trans_a, trans_b, c_dtype, epilogue)) {
+    VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
+    return gemm_bf16_tc(a, b, c, c2, bias, M, N, K, trans_a, trans_b, c_dtype, epilogue, accumulate, (cudaStream_t)stream);
+  }
+  VRR_REQUIRE(impl != VRR_IMPL_TCGEN05 || dtype != VRR_BF16, VRR_ERR_UNSUPPORTED,
+              "gemm_ex: tcgen05 kernel forced but M=%d N=%d K=%d (trans %d/%d) needs N %% 8 == 0, K %% 8 == 0 "
+              "(M %% 8 == 0 when trans_a)", M, N, K, trans_a, trans_b);
+  VRR_REQUIRE(!accumulate, VRR_ERR_UNSUPPORTED, "gemm_ex: accumulate is implemented by the tcgen05 kernel only");
+  VRR_COUNT_FAMILY(VRR_IMPL_SIMT);
+  if (epilogue != VRR_EPI_NONE) {
+    VRR_REQUIRE(c_dtype == dtype, VRR_ERR_UNSUPPORTED, "gemm_ex (SIMT): the bias epilogues need c_dtype == dtype");
+    return gemm_simt_bias(a, b, c, c2, bias, M, N, K, trans_a, trans_b, dtype, epilogue == VRR_EPI_BIAS_GELU,
+                          (cudaStream_t)stream);
+  }
   return gemm_simt(a, b, c, M, N, K, trans_a, trans_b, dtype, c_dtype, (cudaStream_t)stream);
 }
 

@@ -10,8 +10,9 @@ construction (citations: /root/reference/models/vit.py).  What changes is undern
 * qkv Linear + head split + RoPE + cls re-concat    -> one GEMM with RoPE epilogue (vit.py:47-68)
 * QK^T, scale, RPE / Poly-RPE bias, softmax, PV, merge -> one fused attention kernel (vit.py:71-88)
 
-LayerNorm runs the library's fused kernel (first of the "next" rows); the
-output projection, the MLP and the head stay ``torch.nn``.  CUDA sm_100 only: CPU inputs raise; there is no fallback path.
+LayerNorm (fused with the residual adds), the output projection, the MLP (bias + GELU in the fc1 GEMM epilogue)
+and the head run library kernels too: the forward and backward contain no cuBLAS
+GEMM.  CUDA sm_100 only: CPU inputs raise; there is no fallback path.
 """
 import torch
 import torch.nn as nn
@@ -36,7 +37,8 @@ class Mlp(nn.Module):
 
     def forward(self, x):
         if ops.can_fuse_mlp(x, self):
-            return ops.mlp(x, self.fc1, self.fc2)
+            dt = ops.compute_dtype(x)
+            return ops.mlp(x, self.fc1, self.fc2, ops.lp_weight(self.fc1.weight, dt), ops.lp_weight(self.fc2.weight, dt))
         return self.drop2(self.fc2(self.drop1(self.act(self.fc1(x)))))
 
 
@@ -70,9 +72,10 @@ class Attention(nn.Module):
             bias_mode, bias_param = _lib.BIAS_TABLE, pe.relative_position_bias_table
         elif isinstance(pe, PolynomialRPE):
             bias_mode, bias_param, bias_grid = _lib.BIAS_POLY, pe.coefficients, pe.grid_size
-        planes = ops.qkv_rope(x, self.qkv.weight, cos, sin, self.num_heads)
+        dt = ops.compute_dtype(x)
+        planes = ops.qkv_rope(x, self.qkv.weight, cos, sin, self.num_heads, ops.lp_weight(self.qkv.weight, dt))
         out = ops.fused_attention(planes, self.scale, bias_mode, bias_param, bias_grid)
-        return self.proj_drop(ops.linear(out, self.proj))
+        return self.proj_drop(ops.linear(out, self.proj, ops.lp_weight(self.proj.weight, dt)))
 
     def set_pos_encoding(self, pos_encoding):
         self.pos_encoding = pos_encoding  # registers the shared PE module as a child (state_dict dups)
@@ -170,6 +173,8 @@ class VisionTransformer(nn.Module):
         """[B, C, H, W] -> [B, N, E] with N = (H/P)(W/P) + 1 taken from the input (vit.py:235-271)."""
         B, C, H, W = x.shape
         h, w = H // self.patch_size, W // self.patch_size
+        if x.is_cuda:  # one multi-tensor refresh of the bf16 weight copies per forward (no-op in fp32)
+            ops.refresh_lp_weights(self._gemm_weights(), ops.compute_dtype(x))
         abs_table = self.pos_embed.pos_embed if self.use_pos_embed_in_forward else None
         # (under autocast the token stream comes back fp32, like the reference's cat with the fp32 cls token)
         x = ops.patch_embed(x, self.patch_embed.weight, self.patch_embed.bias, self.cls_token,
@@ -196,6 +201,14 @@ class VisionTransformer(nn.Module):
                 x = x + m
         return x
 
+    def _gemm_weights(self):
+        ws = [self.head.weight]
+        for blk in self.blocks:
+            ws += [blk.attn.qkv.weight, blk.attn.proj.weight]
+            if isinstance(blk.mlp, Mlp):
+                ws += [blk.mlp.fc1.weight, blk.mlp.fc2.weight]
+        return ws
+
     def _fusable(self, x):
         return len(self.blocks) > 0 and all(
             type(blk) is Block and isinstance(blk.drop_path, nn.Identity)
@@ -206,4 +219,5 @@ class VisionTransformer(nn.Module):
         x = self.forward_features(x)
         # LayerNorm is per token and only the cls token reaches the head (vit.py:284-285): normalising
         # that row alone gives identical logits and gradients
-        return ops.linear(ops.layer_norm(x[:, 0], self.norm), self.head)
+        y = ops.layer_norm(x[:, 0], self.norm)
+        return ops.linear(y, self.head, ops.lp_weight(self.head.weight, ops.compute_dtype(y)))

@@ -11,6 +11,7 @@ PyTorch is used for device memory, streams and autograd plumbing only; all arith
 paths runs in the hand-written sm_100a kernels.  CUDA only - CPU tensors raise.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -46,6 +47,44 @@ def _stream():
 
 def _f32c(t):
     return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+# ---- low-precision weight cache ---------------------------------------------------------------------
+# Under autocast the reference re-casts every fp32 weight to bf16 in every forward (~60 small cast kernels per
+# ViT-B step).  Here the model asks once per forward: the bf16 copies of all its GEMM weights are refreshed by
+# ONE multi-tensor copy, and only when a master weight changed (its version counter moved) - i.e. once per
+# optimizer step.  The GEMM Functions take the fp32 master (it receives the fp32 weight gradient straight from
+# the dW GEMM) plus this copy.
+_LP = {}  # id(param) -> [weakref(param), version at last refresh, low-precision copy]
+
+
+def refresh_lp_weights(params, dt):
+    src, dst = [], []
+    capturing = torch.cuda.is_current_stream_capturing()
+    for p in params:
+        if p.dtype == dt or not p.is_cuda:
+            continue
+        ent = _LP.get(id(p))
+        if ent is None or ent[0]() is not p or ent[2].device != p.device or ent[2].dtype != dt or ent[2].shape != p.shape:
+            ent = [weakref.ref(p), -1, torch.empty_like(p, dtype=dt, memory_format=torch.contiguous_format)]
+            _LP[id(p)] = ent
+        if capturing or ent[1] != p._version:  # a captured step must always contain its own refresh
+            src.append(p.detach())
+            dst.append(ent[2])
+            ent[1] = p._version
+    if dst:
+        torch._foreach_copy_(dst, src)
+    if len(_LP) > 4096:  # drop entries of dead parameters
+        for k in [k for k, e in _LP.items() if e[0]() is None]:
+            del _LP[k]
+
+
+def lp_weight(p, dt):
+    """The cached ``dt`` copy of parameter ``p`` if :func:`refresh_lp_weights` holds a current one, else None."""
+    ent = _LP.get(id(p))
+    if ent is None or ent[0]() is not p or ent[2].dtype != dt or ent[1] != p._version or ent[2].device != p.device:
+        return None
+    return ent[2]
 
 
 # bench.py sets this to a list to time individual kernel launches with CUDA events recorded on the
@@ -121,9 +160,9 @@ class PatchEmbedFn(torch.autograd.Function):
         d_tokens = d_tokens.contiguous()
         dev = images.device
         K = C * patch * patch
-        # bf16: the weight gradient is a plain GEMM d_tokens^T . unfold(images) -> cuBLAS (allowed for
-        # library-shaped GEMMs); fp32: the library's FFMA split-K GEMM with the unfold fused in.
-        own_dw = not (dt == torch.bfloat16 and patch % 8 == 0 and Wi % 4 == 0)
+        # bf16: the weight gradient is the GEMM d_tokens^T . unfold(images) on the tcgen05 kernel (fp32 result,
+        # split over the B*Np rows); fp32: the library's FFMA split-K GEMM with the unfold fused in.
+        own_dw = not (dt == torch.bfloat16 and patch % 8 == 0 and Wi % 4 == 0 and E % 8 == 0)
         d_w = torch.empty(E, K, device=dev, dtype=torch.float32) if own_dw else None
         d_b = torch.empty(E, device=dev, dtype=torch.float32)
         d_cls = torch.empty(E, device=dev, dtype=torch.float32)
@@ -137,8 +176,7 @@ class PatchEmbedFn(torch.autograd.Function):
                 _lib.check(lib.vrr_patch_unfold(_ptr(images), _ptr(unf), B, C, Hi, Wi, patch, _DT[idt], _stream()),
                            "vrr_patch_unfold")
                 g = d_tokens[:, 1:, :].reshape(B * Np, E).to(torch.bfloat16)
-                with torch.autocast("cuda", enabled=False):
-                    d_w = torch.matmul(g.t(), unf)
+                d_w = _gemm(g, unf, True, False, torch.float32, name="patch_dw")
         d_pos = None
         if pos_shape is not None:
             d_pos = torch.zeros(pos_shape, device=dev, dtype=tdt)
@@ -181,14 +219,17 @@ class QkvRopeFn(torch.autograd.Function):
     """planes[3, B, H, N, Dh] = split_heads(x @ w_qkv^T), q/k rows 1.. rotated in the GEMM epilogue."""
 
     @staticmethod
-    def forward(ctx, x, w_qkv, cos, sin, num_heads):
+    def forward(ctx, x, w_qkv, cos, sin, num_heads, w_lp=None):
+        """``w_qkv`` receives the gradient (fp32 master weight or a tensor already in x's dtype); ``w_lp`` is an
+        optional ready-made copy of it in x's dtype (the model's bf16 weight cache)."""
         _require_cuda(x, w_qkv, cos, sin)
         lib = _lib.load()
         B, N, E = x.shape
         H, Dh = num_heads, E // num_heads
         mode = _rope_args(cos, sin, H, N, Dh)
         x = x.contiguous()
-        w = w_qkv.detach().contiguous()
+        w = (w_lp if w_lp is not None else w_qkv.detach().to(x.dtype)).detach().contiguous()
+        ctx.w_grad_dtype = w_qkv.dtype
         cos32, sin32 = _f32c(cos), _f32c(sin)
         planes = torch.empty(3, B, H, N, Dh, device=x.device, dtype=x.dtype)
         with torch.cuda.device(x.device), _timed("qkv_rope_fwd"):
@@ -215,34 +256,40 @@ class QkvRopeFn(torch.autograd.Function):
                        "vrr_qkv_rope_bwd")
             dx = dw = None
             if ctx.needs_input_grad[0]:
-                dx = _gemm(d_qkv, w, False, False, dt).view(B, N, E)          # [BN,3E] . [3E,E]
+                dx = _gemm(d_qkv, w, False, False, dt, name="qkv_dx").view(B, N, E)            # [BN,3E] . [3E,E]
             if ctx.needs_input_grad[1]:
-                dw = _gemm(d_qkv, x.view(B * N, E), True, False, dt)          # [3E,BN] . [BN,E]
+                dw = _gemm(d_qkv, x.view(B * N, E), True, False, ctx.w_grad_dtype, name="qkv_dw")  # [3E,BN] . [BN,E]
         if need_cs:
             d_cos, d_sin = d_cos.to(cs_dtypes[0]), d_sin.to(cs_dtypes[1])
-        return dx, dw, d_cos, d_sin, None
+        return dx, dw, d_cos, d_sin, None, None
 
 
-def _gemm(a, b, trans_a, trans_b, out_dtype):
-    """Plain projection-backward GEMM.  fp32: the library's FFMA kernel (exact fp32 products, no
-    TF32).  bf16: cuBLAS through torch.matmul - a plain library GEMM with no fused work, which the
-    build rules allow; fp32 accumulation, bf16 result."""
-    if a.dtype == torch.float32:
-        lib = _lib.load()
-        M = a.shape[1] if trans_a else a.shape[0]
-        K = a.shape[0] if trans_a else a.shape[1]
-        N = b.shape[0] if trans_b else b.shape[1]
-        c = torch.empty(M, N, device=a.device, dtype=torch.float32)
-        _lib.check(lib.vrr_gemm(_ptr(a), _ptr(b), _ptr(c), M, N, K, int(trans_a), int(trans_b), _lib.VRR_F32,
-                                _lib.VRR_F32, _stream()), "vrr_gemm")
-        return c.to(out_dtype)
-    with torch.autocast("cuda", enabled=False):
-        return torch.matmul(a.t() if trans_a else a, b.t() if trans_b else b)
+def _gemm(a, b, trans_a, trans_b, out_dtype, bias=None, epilogue=_lib.EPI_NONE, out2=False, name="gemm"):
+    """C = op(A) . op(B) in the library's kernels (``vrr_gemm_ex``) - no cuBLAS anywhere on the path.
+
+    op(A) is [M][K] (trans_a: A stored [K][M]); op(B) is [K][N] (trans_b: B stored [N][K]).  bf16 operands
+    run the tcgen05 CTA-pair kernel (fp32 accumulation; result in ``out_dtype``: bf16, or fp32 for weight
+    gradients), fp32 operands the exact-fp32 FFMA kernel (no TF32).  ``epilogue``: fused ``+ bias`` or
+    ``+ bias, GELU`` (``out2``: also return gelu(C))."""
+    lib = _lib.load()
+    M = a.shape[1] if trans_a else a.shape[0]
+    K = a.shape[0] if trans_a else a.shape[1]
+    N = b.shape[0] if trans_b else b.shape[1]
+    a, b = a.contiguous(), b.contiguous()
+    c = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    c2 = torch.empty_like(c) if out2 else None
+    bias32 = _f32c(bias) if epilogue != _lib.EPI_NONE else None
+    with _timed(name):
+        _lib.check(lib.vrr_gemm_ex(_ptr(a), _ptr(b), _ptr(c), _ptr(c2), _ptr(bias32), M, N, K, int(trans_a), int(trans_b),
+                                   _DT[a.dtype], _DT[out_dtype], int(epilogue), 0, _stream()), "vrr_gemm_ex")
+    return (c, c2) if out2 else c
 
 
-def qkv_rope(x, w_qkv, cos, sin, num_heads):
+def qkv_rope(x, w_qkv, cos, sin, num_heads, w_lp=None):
     dt = compute_dtype(x)
-    return QkvRopeFn.apply(x.to(dt), w_qkv.to(dt), cos, sin, num_heads)
+    if w_lp is not None and w_lp.dtype != dt:
+        w_lp = None
+    return QkvRopeFn.apply(x.to(dt), w_qkv, cos, sin, num_heads, w_lp)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -437,76 +484,99 @@ def _colsum(t2d):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b with the GEMMs on cuBLAS (plain library GEMMs, bias fused in its epilogue) and the
-    bias gradient on the library's column-sum kernel (out-proj / head, models/vit.py:91,285)."""
+    """y = x W^T + b (out-proj / head, models/vit.py:91,285).  bf16: forward GEMM with the bias in its
+    epilogue, dX and dW (fp32, straight into the master-weight gradient) on the tcgen05 CTA-pair kernel;
+    bias gradient on the column-sum kernel.  ``w`` / ``b`` receive the gradients (fp32 masters or tensors in
+    x's dtype); ``w_lp`` is an optional ready-made copy of ``w`` in x's dtype."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
-        y = torch.nn.functional.linear(x, w, b)
-        ctx.save_for_backward(x, w)
-        ctx.has_bias = b is not None
-        return y
+    def forward(ctx, x, w, b, w_lp=None):
+        _require_cuda(x, w, b)
+        dt = x.dtype
+        wl = (w_lp if w_lp is not None else w.detach().to(dt)).detach()
+        x2 = x.reshape(-1, x.shape[-1])
+        y = _gemm(x2, wl, False, True, dt, bias=b, epilogue=_lib.EPI_BIAS if b is not None else _lib.EPI_NONE,
+                  name="linear_fwd")
+        ctx.save_for_backward(x2, wl)
+        ctx.meta = (x.shape, w.dtype, None if b is None else b.dtype)
+        return y.view(*x.shape[:-1], wl.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x2, wl = ctx.saved_tensors
+        x_shape, w_dtype, b_dtype = ctx.meta
         dy2 = dy.contiguous().view(-1, dy.shape[-1])
-        x2 = x.reshape(-1, x.shape[-1])
-        with torch.cuda.device(dy.device), torch.autocast("cuda", enabled=False):
-            dx = (dy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
-            dw = dy2.t() @ x2 if ctx.needs_input_grad[1] else None
-            db = None
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+        if dy2.dtype != x2.dtype:
+            dy2 = dy2.to(x2.dtype)
+        dx = dw = db = None
+        with torch.cuda.device(dy.device):
+            if ctx.needs_input_grad[0]:
+                dx = _gemm(dy2, wl, False, False, x2.dtype, name="linear_dx").view(x_shape)
+            if ctx.needs_input_grad[1]:
+                dw = _gemm(dy2, x2, True, False, w_dtype, name="linear_dw")
+            if b_dtype is not None and ctx.needs_input_grad[2]:
                 with _timed("colsum"):
-                    db = _colsum(dy2).to(dy.dtype)
-        return dx, dw, db
+                    db = _colsum(dy2).to(b_dtype)
+        return dx, dw, db, None
 
 
 class MlpFn(torch.autograd.Function):
-    """fc1 -> exact GELU -> fc2 (timm Mlp, models/vit.py:118).  GEMMs on cuBLAS; the backward runs
-    gelu' fused with the fc1 bias-gradient reduction, and the fc2 bias gradient on the column-sum kernel."""
+    """fc1 -> exact GELU -> fc2 (timm Mlp, models/vit.py:118).  bf16: fc1 with bias + GELU fused in the GEMM
+    epilogue (h and gelu(h) both written: the backward needs h), fc2 with its bias; backward = four GEMMs on the
+    same kernel (dW in fp32) + gelu' fused with the fc1 bias-gradient reduction + one column sum."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
-        h = torch.nn.functional.linear(x, w1, b1)
-        a = torch.nn.functional.gelu(h)
-        y = torch.nn.functional.linear(a, w2, b2)
-        ctx.save_for_backward(x, h, a, w1, w2)
-        return y
+    def forward(ctx, x, w1, b1, w2, b2, w1_lp=None, w2_lp=None):
+        _require_cuda(x, w1, b1, w2, b2)
+        dt = x.dtype
+        w1l = (w1_lp if w1_lp is not None else w1.detach().to(dt)).detach()
+        w2l = (w2_lp if w2_lp is not None else w2.detach().to(dt)).detach()
+        x2 = x.reshape(-1, x.shape[-1])
+        h, a = _gemm(x2, w1l, False, True, dt, bias=b1, epilogue=_lib.EPI_BIAS_GELU, out2=True, name="fc1_fwd")
+        y = _gemm(a, w2l, False, True, dt, bias=b2, epilogue=_lib.EPI_BIAS, name="fc2_fwd")
+        ctx.save_for_backward(x2, h, a, w1l, w2l)
+        ctx.meta = (x.shape, w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        return y.view(*x.shape[:-1], w2l.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
-        x, h, a, w1, w2 = ctx.saved_tensors
+        x2, h2, a2, w1l, w2l = ctx.saved_tensors
+        x_shape, w1_dt, b1_dt, w2_dt, b2_dt = ctx.meta
         dy2 = dy.contiguous().view(-1, dy.shape[-1])
-        x2, h2, a2 = x.reshape(-1, x.shape[-1]), h.view(-1, h.shape[-1]), a.view(-1, a.shape[-1])
+        if dy2.dtype != x2.dtype:
+            dy2 = dy2.to(x2.dtype)
         M, C = h2.shape
-        with torch.cuda.device(dy.device), torch.autocast("cuda", enabled=False):
-            da = dy2 @ w2
-            dw2 = dy2.t() @ a2
+        with torch.cuda.device(dy.device):
+            da = _gemm(dy2, w2l, False, False, x2.dtype, name="fc2_dx")
+            dw2 = _gemm(dy2, a2, True, False, w2_dt, name="fc2_dw")
             with _timed("colsum"):
-                db2 = _colsum(dy2).to(dy.dtype)
+                db2 = _colsum(dy2).to(b2_dt)
             dh = torch.empty_like(h2)
             db1 = torch.empty(C, device=dy.device, dtype=torch.float32)
             with _timed("gelu_bwd"):
                 _lib.check(lib.vrr_gelu_bwd(_ptr(da), _ptr(h2), _ptr(dh), _ptr(db1), M, C, _DT[h2.dtype], _stream()),
                            "vrr_gelu_bwd")
-            dx = (dh @ w1).view(x.shape)
-            dw1 = dh.t() @ x2
-        return dx, dw1, db1.to(dy.dtype), dw2, db2
+            dx = _gemm(dh, w1l, False, False, x2.dtype, name="fc1_dx").view(x_shape)
+            dw1 = _gemm(dh, x2, True, False, w1_dt, name="fc1_dw")
+        return dx, dw1, db1.to(b1_dt), dw2, db2, None, None
 
 
-def linear(x, lin: torch.nn.Linear):
+def linear(x, lin: torch.nn.Linear, w_lp=None):
     """``lin(x)`` through :class:`LinearFn` (CUDA, bias, supported dtype, width % 4 == 0) else the module."""
     if not (x.is_cuda and lin.bias is not None and lin.out_features % 4 == 0 and x.dtype in _DT):
         return lin(x)
     dt = compute_dtype(x)
-    return LinearFn.apply(x.to(dt), lin.weight.to(dt), lin.bias.to(dt))
+    if w_lp is not None and w_lp.dtype != dt:
+        w_lp = None
+    return LinearFn.apply(x.to(dt), lin.weight, lin.bias, w_lp)
 
 
-def mlp(x, fc1: torch.nn.Linear, fc2: torch.nn.Linear):
+def mlp(x, fc1: torch.nn.Linear, fc2: torch.nn.Linear, w1_lp=None, w2_lp=None):
     dt = compute_dtype(x)
-    return MlpFn.apply(x.to(dt), fc1.weight.to(dt), fc1.bias.to(dt), fc2.weight.to(dt), fc2.bias.to(dt))
+    if w1_lp is not None and (w1_lp.dtype != dt or w2_lp is None or w2_lp.dtype != dt):
+        w1_lp = w2_lp = None
+    return MlpFn.apply(x.to(dt), fc1.weight, fc1.bias, fc2.weight, fc2.bias, w1_lp, w2_lp)
 
 
 def can_fuse_mlp(x, m) -> bool:
