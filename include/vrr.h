@@ -94,10 +94,11 @@ uint64_t vrr_launch_count(void);
 uint64_t vrr_family_count(int family);
 /* Tuning / experiment switches (process-wide): "attn_fwd_table_bulk" (0/1),
  * "attn_fwd_rescale_threshold_x100", "gemm_variant" (2 = CTA-pair kernels, default; 1 = 1-CTA kernels for the
- * QKV / patch-embed GEMMs, kept for A/B measurements). */
+ * QKV / patch-embed GEMMs, kept for A/B measurements), "attn_fwd_variant" / "attn_bwd_variant" (3 = persistent
+ * kernels, default; 2 = one CTA per 128-row tile, kept for A/B measurements). */
 int vrr_set_option(const char* name, int value);
-/* Debug: one CTA of the next attention-forward launches records clock64() phase stamps (8 per key
- * tile, first 8 tiles) into `device_buf` (64 x int64); NULL switches it off. */
+/* Debug: CTA 0 of the next attention launches records clock64() phase stamps of its producer, issuer and
+ * softmax roles into `device_buf` (1024 x int64, zero it first); NULL switches it off. */
 int vrr_debug_timestamps(void* device_buf);
 
 /* ---- (c) patch embedding: models/vit.py:164,248-258 ---------------------------------------- */

@@ -140,9 +140,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erf_v);
 }
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, class Epi>
