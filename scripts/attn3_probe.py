@@ -103,7 +103,11 @@ if "fwd" in what or "bwd" in what:
             if b * h > 100 and kind == "poly_perhead":
                 continue
             t0 = time.time()
-            all_ok = check(b, h, n, kind, bwd) and all_ok
+            try:
+                all_ok = check(b, h, n, kind, bwd) and all_ok
+            except RuntimeError as e:
+                print(f"FAIL B={b} H={h} N={n} {kind}: {e}", flush=True)
+                all_ok = False
             if time.time() - t0 > 60:
                 print("slow case - stopping", flush=True)
                 sys.exit(2)

@@ -39,6 +39,12 @@ int attn_bwd_tc2(const void* planes, const vrr_bias_desc* bias, const void* out,
                  void* d_planes, float* d_bias_param, float* delta, int B, int H, int N, int Dh, float scale,
                  cudaStream_t st);
 
+// attn_bwd_ws.cu (whole-sequence fused backward for N <= 256, no bias: one persistent kernel, operands read once)
+bool attn_bwd_ws_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
+void attn_bwd_ws_set_debug(long long* buf);
+int attn_bwd_ws(const void* planes, const void* out, const void* d_out, const float* lse, void* d_planes, int B, int H,
+                int N, int Dh, float scale, cudaStream_t st);
+
 // gemm_simt.cu
 int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
                       int B, int N, int E, int H, int rope_mode, int dtype, cudaStream_t st);

@@ -49,6 +49,20 @@ int require_device() {
     set_error("device ordinal %d out of range", dev);
     return VRR_ERR_NO_DEVICE;
   }
+  // Driver-API calls made by the launchers (cuTensorMapEncodeTiled) need the primary context CURRENT in the
+  // calling thread.  A runtime call that touches the device binds it; cudaGetDevice does not.  PyTorch's autograd
+  // worker threads reach this library without one when their allocations are served from the caching allocator
+  // (observed: CUDA_ERROR_INVALID_CONTEXT from the first backward of a process) - bind once per thread.
+  static thread_local int bound_dev = -1;
+  if (bound_dev != dev) {
+    e = cudaFree(nullptr);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cannot initialise the CUDA context of device %d: %s", dev, cudaGetErrorString(e));
+      return VRR_ERR_NO_DEVICE;
+    }
+    bound_dev = dev;
+  }
   const int state = g_dev_state[dev].load(std::memory_order_acquire);
   if (state == 1) return VRR_OK;
   int major = 0, minor = 0, sms = 0;
@@ -125,6 +139,7 @@ uint64_t vrr_family_count(int family) {
 int vrr_debug_timestamps(void* device_buf) {  /* 64 x int64 device buffer, or NULL to switch off */
   attn_fwd_tc_set_debug((long long*)device_buf);
   attn_fwd_tc3_set_debug((long long*)device_buf);
+  attn_bwd_ws_set_debug((long long*)device_buf);
   return VRR_OK;
 }
 int vrr_set_option(const char* name, int value) {
@@ -349,6 +364,8 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
   const int impl = g_impl.load();
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_bwd_tc2_supported(B, H, N, Dh, bias)) {
     VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
+    if (g_attn_bwd_variant.load() >= 3 && attn_bwd_ws_supported(B, H, N, Dh, bias))
+      return attn_bwd_ws(planes, out, d_out, lse, d_planes, B, H, N, Dh, scale, (cudaStream_t)stream);
     return attn_bwd_tc2(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
                         (cudaStream_t)stream);
   }
