@@ -24,9 +24,9 @@ _lib.check(lib.vrr_debug_timestamps(None), "dbg")
 v = buf.cpu().view(4, 256)
 t0 = int(v[v > 0].min())
 names = ["group 0 per pass (wait_s, s_ready, p_arrived, acc_ready)", "group 1 per pass",
-         "issuer per pass (start, S/dP issued, P[0] ready, acc[0] issued, P[1] ready, acc[1] issued)", "-"]
-per = [4, 4, 8, 2]
-for reg in range(3):
+         "issuer per pass (start, S/dP issued, P[0] ready, acc[0] issued, P[1] ready, acc[1] issued)", "group 0 epilogue per lane tile (acc wait done, ld done, arrived, first store done)"]
+per = [4, 4, 8, 4]
+for reg in range(4):
     print(names[reg])
     row = v[reg]
     for i in range(0, 256, per[reg]):

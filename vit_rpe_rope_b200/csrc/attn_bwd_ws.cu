@@ -1,5 +1,5 @@
-// Fused attention backward for SHORT sequences (N <= 256), one persistent kernel: the whole-sequence variant.
-// Autograd of models/vit.py:71-88 of the reference:
+// Fused attention backward for SHORT sequences (round16(N) <= 208: the 65..197-token ViT configurations), one
+// persistent kernel: the whole-sequence variant.  Autograd of models/vit.py:71-88 of the reference:
 //   P = softmax(S), dV = P^T dO, dP = dO V^T, dS = P o (dP - delta), dQ = scale dS K, dK = scale dS^T Q.
 //
 // Variant 2 (attn_bwd_tc2.cu) is two kernels (dQ; dK/dV) that each read Q, K, V, dO from HBM (1.44x the algorithmic
@@ -8,15 +8,19 @@
 //   * one CTA per SM loops over work items (image, head); Q, K, V, dO of the NEXT item are prefetched by TMA into the
 //     other half of shared memory (2 x 4 x N x 128 B) while the current one is processed: every operand is read from
 //     HBM exactly once per launch;
-//   * an item is a sequence of PASSES over 128 TMEM lanes against ALL columns at once:
-//       dQ pass (lane = query row i, one per 128 rows):  S = Q K^T, dP = dO V^T  ->  dS  ->  dQ = dS K
-//       dKV pass (lane = key j, one per 128 keys):       S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T  ->  dV, dK
-//     i.e. 8 + ~26 large tcgen05.mma and ONE softmax-side round trip per pass instead of one per 32 columns;
-//   * the columns of a pass are split into two halves owned by the two compute warpgroups (the big half
-//     alternates), each half with its own "S ready" / "P ready" barriers, so one group's exponentials overlap the
-//     other's MMAs; P / dS are written back in place (bf16) and consumed from TMEM by the accumulating MMAs;
-//   * TMEM (512 columns): S at [0,256), dP at [256,512); the accumulators (dQ, or dK and dV) live in columns
-//     [64,128) / [320,384) of the first half - S / dP columns that half's owner has already consumed;
+//   * an item is a set of LANE TILES (128 TMEM lanes against all columns):
+//       dQ tile  (lane = query row i):  S = Q K^T, dP = dO V^T  ->  dS            ->  dQ = dS K
+//       dKV tile (lane = key j):        S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T   ->  dV = P^T dO, dK = dS^T Q
+//     processed in two or three COLUMN GROUPS (128 columns, then <= 96 / <= 64) of large tcgen05.mma (N up to 128)
+//     with ONE softmax-side round trip each, instead of one per 32 columns;
+//   * the two compute warpgroups are independent streams: each owns half of TMEM (256 columns), its own issuer warp
+//     and its own lane tiles (group w: the dQ tiles of parity w and the dKV tiles of parity 1 - w), so one group's
+//     exponentials overlap the other's MMAs and epilogue;
+//   * per stream TMEM: S at [0,128), dP at [128,256) for the first column group; P / dS are written back in place
+//     (bf16) and consumed from TMEM by the accumulating MMAs; the accumulators live in columns the group has already
+//     consumed (dQ or dV at [192,256), dK at [64,128)); later column groups reuse [0,96) / [96,192) (dQ) or
+//     [0,64) / [128,192) (dKV) - the tensor pipe executes in issue order, so a group's S MMAs may be issued right
+//     behind the accumulating MMAs that read the columns they overwrite;
 //   * delta = rowsum(dO o O) and lse*log2(e) of the NEXT item are computed by a helper warp into shared memory
 //     while the current item runs (rows past N get lse = +inf -> P = 0).
 // Bias modes (relative table / polynomial) stay on variant 2 for now.
@@ -31,11 +35,10 @@ using namespace tc;
 namespace {
 
 constexpr int kDh = 64;
-constexpr int kThreads = 384;   // warps 0-3 / 4-7 compute groups, 8 producer, 9 issuer, 10 statistics helper, 11 idle
+constexpr int kThreads = 384;   // warps 0-3 / 4-7 compute streams, 8 producer, 9 / 10 issuers, 11 statistics helper
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColDP = 256, kAcc1 = 64, kAcc2 = 320;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kNumBars = 12;
+constexpr int kNumBars = 14;
 constexpr int kSmemMax = 232448;
 
 struct BwsParams {
@@ -52,80 +55,103 @@ __device__ __forceinline__ void dbg_stamp(const BwsParams& p, int region, int id
   if (p.dbg != nullptr && blockIdx.x == 0 && idx < 256) p.dbg[region * 256 + idx] = clock64();
 }
 
-__device__ __forceinline__ void store_half_row(__nv_bfloat16* dst, const uint32_t (&v)[32], float mul) {
+// Store this thread's row (64 fp32 channels in two 32-register halves) as 128 bytes of bf16.
+__device__ __forceinline__ void store_row(__nv_bfloat16* dst, const uint32_t (&lo)[32], const uint32_t (&hi)[32], float mul) {
 #pragma unroll
   for (int v8 = 0; v8 < 4; ++v8) {
     uint4 w;
-    w.x = pack_bf16(__uint_as_float(v[v8 * 8 + 0]) * mul, __uint_as_float(v[v8 * 8 + 1]) * mul);
-    w.y = pack_bf16(__uint_as_float(v[v8 * 8 + 2]) * mul, __uint_as_float(v[v8 * 8 + 3]) * mul);
-    w.z = pack_bf16(__uint_as_float(v[v8 * 8 + 4]) * mul, __uint_as_float(v[v8 * 8 + 5]) * mul);
-    w.w = pack_bf16(__uint_as_float(v[v8 * 8 + 6]) * mul, __uint_as_float(v[v8 * 8 + 7]) * mul);
+    w.x = pack_bf16(__uint_as_float(lo[v8 * 8 + 0]) * mul, __uint_as_float(lo[v8 * 8 + 1]) * mul);
+    w.y = pack_bf16(__uint_as_float(lo[v8 * 8 + 2]) * mul, __uint_as_float(lo[v8 * 8 + 3]) * mul);
+    w.z = pack_bf16(__uint_as_float(lo[v8 * 8 + 4]) * mul, __uint_as_float(lo[v8 * 8 + 5]) * mul);
+    w.w = pack_bf16(__uint_as_float(lo[v8 * 8 + 6]) * mul, __uint_as_float(lo[v8 * 8 + 7]) * mul);
     *reinterpret_cast<uint4*>(dst + v8 * 8) = w;
   }
+#pragma unroll
+  for (int v8 = 0; v8 < 4; ++v8) {
+    uint4 w;
+    w.x = pack_bf16(__uint_as_float(hi[v8 * 8 + 0]) * mul, __uint_as_float(hi[v8 * 8 + 1]) * mul);
+    w.y = pack_bf16(__uint_as_float(hi[v8 * 8 + 2]) * mul, __uint_as_float(hi[v8 * 8 + 3]) * mul);
+    w.z = pack_bf16(__uint_as_float(hi[v8 * 8 + 4]) * mul, __uint_as_float(hi[v8 * 8 + 5]) * mul);
+    w.w = pack_bf16(__uint_as_float(hi[v8 * 8 + 6]) * mul, __uint_as_float(hi[v8 * 8 + 7]) * mul);
+    *reinterpret_cast<uint4*>(dst + 32 + v8 * 8) = w;
+  }
 }
 
-// dQ pass, W (32 or 16) columns = keys j0 .. j0+W-1 of this thread's query row:
-//   dS = exp2(S c - lse2) (dP - delta), keys past N masked; dS (bf16 pairs) over the S columns.
-template <int W>
-__device__ __forceinline__ void dq_chunk(const BwsParams& p, uint32_t t_s, uint32_t t_dp, uint32_t t_dst, int j0,
-                                         float neg_lse2, float delta) {
-  uint32_t s[W], d[W], packed[W / 2];
-  if constexpr (W == 32) {
-    tmem_ld32(t_s, s);
-    tmem_ld32(t_dp, d);
-  } else {
-    tmem_ld16(t_s, s);
-    tmem_ld16(t_dp, d);
-  }
-  tmem_wait_ld();
-  const bool full = j0 + W <= p.N;
+// One column group of a lane tile for one thread (= one TMEM lane), 16 accumulator columns at a time with the NEXT
+// 16 columns' tcgen05.ld in flight while the current ones are processed (two register buffers, A / B).
+//   DQ  (lane = query row i, column = key j):  dS = exp2(S c - lse2_i) (dP - delta_i), keys past N masked;
+//        dS (bf16 pairs) written over the S columns.
+//   !DQ (lane = key j, column = query row i):  per-column (lse2_i, delta_i) from shared memory (lse2 = +inf past N
+//        -> P = 0);  P^T (bf16) over the S^T columns, dS^T (bf16) over the dP^T columns.
+template <bool DQ>
+__device__ __forceinline__ void process16(const BwsParams& p, const uint32_t (&s)[16], const uint32_t (&d)[16], uint32_t t_dst_p,
+                                          uint32_t t_dst_ds, int col0, float neg_lse2, float delta, const float4* stats2) {
+  uint32_t pp[8], pd[8];
+  if (DQ) {
+    const bool full = col0 + 16 <= p.N;
 #pragma unroll
-  for (int e = 0; e < W; e += 2) {
-    float p0 = ex2(fmaf(__uint_as_float(s[e]), p.scale_log2, neg_lse2));
-    float p1 = ex2(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, neg_lse2));
-    if (!full) {
-      p0 = j0 + e < p.N ? p0 : 0.f;
-      p1 = j0 + e + 1 < p.N ? p1 : 0.f;
+    for (int e = 0; e < 16; e += 2) {
+      float p0 = ex2(fmaf(__uint_as_float(s[e]), p.scale_log2, neg_lse2));
+      float p1 = ex2(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, neg_lse2));
+      if (!full) {
+        p0 = col0 + e < p.N ? p0 : 0.f;
+        p1 = col0 + e + 1 < p.N ? p1 : 0.f;
+      }
+      pd[e >> 1] = pack_bf16(p0 * (__uint_as_float(d[e]) - delta), p1 * (__uint_as_float(d[e + 1]) - delta));
     }
-    const float ds0 = p0 * (__uint_as_float(d[e]) - delta);
-    const float ds1 = p1 * (__uint_as_float(d[e + 1]) - delta);
-    packed[e >> 1] = pack_bf16(ds0, ds1);
-  }
-  if constexpr (W == 32) tmem_st16(t_dst, packed);
-  else tmem_st8(t_dst, packed);
-}
-
-// dK/dV pass, W columns = query rows i0 .. i0+W-1 of this thread's key: per-column (lse2, delta) from shared memory;
-//   P^T (bf16) over the S^T columns, dS^T (bf16) over the dP^T columns.
-template <int W>
-__device__ __forceinline__ void dkv_chunk(const BwsParams& p, uint32_t t_s, uint32_t t_dp, uint32_t t_dst_p,
-                                          uint32_t t_dst_ds, const float4* stats2) {
-  uint32_t s[W], d[W], pp[W / 2], pd[W / 2];
-  if constexpr (W == 32) {
-    tmem_ld32(t_s, s);
-    tmem_ld32(t_dp, d);
+    tmem_st8(t_dst_p, pd);
   } else {
-    tmem_ld16(t_s, s);
-    tmem_ld16(t_dp, d);
-  }
-  tmem_wait_ld();
 #pragma unroll
-  for (int e = 0; e < W; e += 2) {
-    const float4 st = stats2[e >> 1];  // (lse2, delta) of rows i0+e and i0+e+1; lse2 = +inf past N -> P = 0
-    const float p0 = ex2(fmaf(__uint_as_float(s[e]), p.scale_log2, -st.x));
-    const float p1 = ex2(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, -st.z));
-    const float ds0 = p0 * (__uint_as_float(d[e]) - st.y);
-    const float ds1 = p1 * (__uint_as_float(d[e + 1]) - st.w);
-    pp[e >> 1] = pack_bf16(p0, p1);
-    pd[e >> 1] = pack_bf16(ds0, ds1);
-  }
-  if constexpr (W == 32) {
-    tmem_st16(t_dst_p, pp);
-    tmem_st16(t_dst_ds, pd);
-  } else {
+    for (int e = 0; e < 16; e += 2) {
+      const float4 st = stats2[e >> 1];  // (lse2, delta) of rows col0+e and col0+e+1
+      const float p0 = ex2(fmaf(__uint_as_float(s[e]), p.scale_log2, -st.x));
+      const float p1 = ex2(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, -st.z));
+      pp[e >> 1] = pack_bf16(p0, p1);
+      pd[e >> 1] = pack_bf16(p0 * (__uint_as_float(d[e]) - st.y), p1 * (__uint_as_float(d[e + 1]) - st.w));
+    }
     tmem_st8(t_dst_p, pp);
     tmem_st8(t_dst_ds, pd);
   }
+}
+
+template <bool DQ>
+__device__ __forceinline__ void process_group(const BwsParams& p, uint32_t t_s, uint32_t t_dp, int n16, int col0, float neg_lse2,
+                                              float delta, const float4* stats2) {
+  // (a version with the next chunk's tcgen05.ld in flight behind a second register buffer measured SLOWER: 3 400 vs
+  // 2 620 cycles per 128 columns - the group is bound by the exponentials, not by the TMEM latency)
+#pragma unroll 1
+  for (int c = 0; c < n16; ++c) {
+    uint32_t s[16], d[16];
+    tmem_ld16(t_s + c * 16, s);
+    tmem_ld16(t_dp + c * 16, d);
+    tmem_wait_ld();
+    process16<DQ>(p, s, d, t_s + c * 8, t_dp + c * 8, col0 + c * 16, neg_lse2, delta, stats2 + c * 8);
+  }
+}
+
+// Column groups of a lane tile: (start column, width, TMEM offset of dP): 128 columns, then <= 96 (dQ) / <= 64 (dKV).
+// Same functions on the issuer and the compute side.
+struct ColGroup {
+  int c0, cw, dp_off;
+};
+__device__ __forceinline__ int num_groups(bool is_dq, int npad) {
+  if (npad <= 128) return 1;
+  const int step = is_dq ? 96 : 64;
+  return 1 + (npad - 128 + step - 1) / step;
+}
+__device__ __forceinline__ ColGroup group_at(bool is_dq, int npad, int gi) {
+  ColGroup g;
+  if (gi == 0) {
+    g.c0 = 0;
+    g.cw = npad < 128 ? npad : 128;
+    g.dp_off = 128;
+  } else {
+    const int step = is_dq ? 96 : 64;
+    g.c0 = 128 + (gi - 1) * step;
+    g.cw = npad - g.c0 < step ? npad - g.c0 : step;
+    g.dp_off = is_dq ? 96 : 128;
+  }
+  return g;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -141,32 +167,29 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_pl64, const __grid_con
   float2* stats = reinterpret_cast<float2*>(smem + 2 * slot_bytes);   // [2 items][256] (lse * log2e, delta)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 512);
   uint64_t* bar_full = bars;              // [2] item data landed
-  uint64_t* bar_empty = bars + 2;         // [2] last MMA of the item retired -> slot reusable
-  uint64_t* bar_sfull = bars + 4;         // [2 halves] S and dP of the half ready
-  uint64_t* bar_pfull = bars + 6;         // [2 halves] P / dS of the half stored (128 arrivals)
-  uint64_t* bar_accfull = bars + 8;       // accumulators of the pass ready
-  uint64_t* bar_accempty = bars + 9;      // epilogue of the pass has read them (256 arrivals)
-  uint64_t* bar_stfull = bars + 10;       // [2] statistics of the item written (32 arrivals)
+  uint64_t* bar_empty = bars + 2;         // [2] last MMA of the item retired in both streams -> slot reusable
+  uint64_t* bar_sfull = bars + 4;         // [2 streams] S and dP of the column group ready
+  uint64_t* bar_pfull = bars + 6;         // [2 streams] P / dS of the column group stored (128 arrivals)
+  uint64_t* bar_accfull = bars + 8;       // [2 streams] accumulators of the lane tile ready
+  uint64_t* bar_accempty = bars + 10;     // [2 streams] epilogue has read them (128 arrivals)
+  uint64_t* bar_stfull = bars + 12;       // [2] statistics of the item written (32 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = p.total_items;
   const int BHN = p.B * H * N;
   const int ntile = (N + 127) >> 7;                // 128-lane tiles of rows / of keys
-  const int cA = npad < 128 ? npad : 128;          // columns of the first half of a pass
-  const int cB = npad - cA;                        // columns of the second half (0: one group idles)
-  const int npass = 2 * ntile;                     // passes per item: ntile dQ passes, then ntile dK/dV passes
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], 2);
       mbar_init(&bar_sfull[s], 1);
       mbar_init(&bar_pfull[s], 128);
+      mbar_init(&bar_accfull[s], 1);
+      mbar_init(&bar_accempty[s], 128);
       mbar_init(&bar_stfull[s], 32);
     }
-    mbar_init(bar_accfull, 1);
-    mbar_init(bar_accempty, 256);
     fence_mbar_init();
   }
   __syncwarp();
@@ -176,6 +199,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_pl64, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // NB: with 230 KB of shared memory the L1 that would absorb register spills is nearly gone - a 184-byte stack frame
+  // cost ~5 000 cycles per lane tile (measured).  Keep `ptxas -v` at 0 spill bytes for this kernel.
   if (warp == 8) {
     // ============================================ TMA producer ============================================
     if (elect_one()) {
@@ -209,81 +234,71 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_pl64, const __grid_con
       }
       __syncwarp();
     }
-  } else if (warp == 9) {
-    // ============================================ MMA issuer ==============================================
+  } else if (warp == 9 || warp == 10) {
+    // ============================================ MMA issuer of stream w ==================================
+    const int w = warp - 9;
+    const uint32_t T = tmem_base + (uint32_t)(w * 256);
     const uint32_t smem_b = smem_u32(smem);
-    uint32_t n = 0;  // global pass counter of this CTA
+    constexpr uint32_t idesc_acc = idesc_bf16(128, kDh, 0, 1);
+    uint32_t ng = 0, nt = 0;  // column groups / lane tiles issued so far by this stream (barrier phases)
     int k = 0;
     for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++k) {
       const int sl = k & 1;
       const uint32_t q_b = smem_b + sl * slot_bytes, k_b = q_b + tbytes, v_b = k_b + tbytes, g_b = v_b + tbytes;
       mbar_wait(&bar_full[sl], (uint32_t)((k >> 1) & 1));
-      for (int ps = 0; ps < npass; ++ps, ++n) {
-        const bool is_dq = ps < ntile;
-        const int tile = is_dq ? ps : ps - ntile;
-        const uint32_t par = n & 1;
-        // lanes: dQ pass -> Q / dO rows of the tile against K / V;  dK/dV pass -> K / V rows against Q / dO
+      for (int lt = 0; lt < 2 * ntile; ++lt) {
+        const bool is_dq = lt < ntile;
+        const int tile = is_dq ? lt : lt - ntile;
+        if (((tile & 1) == w) != is_dq) continue;  // stream w: dQ tiles of parity w, dKV tiles of parity 1 - w
+        // lanes: dQ tile -> Q / dO rows of the tile against K / V;  dKV tile -> K / V rows against Q / dO
         const uint32_t a_s = (is_dq ? q_b : k_b) + tile * 16384, a_p = (is_dq ? g_b : v_b) + tile * 16384;
         const uint32_t b_s = is_dq ? k_b : q_b, b_p = is_dq ? v_b : g_b;
-        mbar_wait(bar_accempty, par ^ 1);  // the previous pass' epilogue has read its accumulators
+        mbar_wait(&bar_accempty[w], (nt & 1) ^ 1);  // the previous lane tile's epilogue has read its accumulators
         tc_fence_after();
-        if (lane == 0) dbg_stamp(p, 2, (int)n * 8 + 0);
-        if (elect_one()) {
-          const uint64_t das = smem_desc_sw128(a_s), dap = smem_desc_sw128(a_p);
-          {
-            const uint32_t idesc = idesc_bf16(128, cA, 0, 0);
-            const uint64_t dbs = smem_desc_sw128(b_s), dbp = smem_desc_sw128(b_p);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma_ss(tmem_base, das + 2 * kk, dbs + 2 * kk, idesc, kk > 0);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma_ss(tmem_base + kColDP, dap + 2 * kk, dbp + 2 * kk, idesc, kk > 0);
-            mma_commit(&bar_sfull[0]);
-          }
-          if (cB > 0) {
-            const uint32_t idesc = idesc_bf16(128, cB, 0, 0);
-            const uint64_t dbs = smem_desc_sw128(b_s + cA * 128), dbp = smem_desc_sw128(b_p + cA * 128);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma_ss(tmem_base + cA, das + 2 * kk, dbs + 2 * kk, idesc, kk > 0);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma_ss(tmem_base + kColDP + cA, dap + 2 * kk, dbp + 2 * kk, idesc, kk > 0);
-            mma_commit(&bar_sfull[1]);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) dbg_stamp(p, 2, (int)n * 8 + 1);
-        constexpr uint32_t idesc_acc = idesc_bf16(128, kDh, 0, 1);
-        // accumulating MMAs of one half: A = P / dS (bf16) from TMEM, B = the column-side operand, MN-major
-        for (int half = 0; half < 2; ++half) {
-          const int c0 = half == 0 ? 0 : cA, cw = half == 0 ? cA : cB;
-          if (cw == 0) break;
-          mbar_wait(&bar_pfull[half], par);
-          tc_fence_after();
-          if (lane == 0) dbg_stamp(p, 2, (int)n * 8 + 2 + 2 * half);
+        const int ngr = num_groups(is_dq, npad);
+        for (int gi = 0; gi < ngr; ++gi) {
+          const ColGroup g = group_at(is_dq, npad, gi);
+          const bool first = gi == 0;
+          const bool last = gi == ngr - 1;
           if (elect_one()) {
-            const int ksteps = cw >> 4;
-            if (is_dq) {
-              const uint64_t dk = smem_desc_sw128(k_b) + (uint64_t)(128 * (c0 >> 4));
-              for (int kk = 0; kk < ksteps; ++kk)
-                mma_ts(tmem_base + kAcc1, tmem_base + c0 + kk * 8, dk + 128 * kk, idesc_acc, (half | kk) != 0);
-            } else {
-              const uint64_t dg = smem_desc_sw128(g_b) + (uint64_t)(128 * (c0 >> 4));
-              const uint64_t dq = smem_desc_sw128(q_b) + (uint64_t)(128 * (c0 >> 4));
-              for (int kk = 0; kk < ksteps; ++kk)  // dV += P^T dO
-                mma_ts(tmem_base + kAcc2, tmem_base + c0 + kk * 8, dg + 128 * kk, idesc_acc, (half | kk) != 0);
-              for (int kk = 0; kk < ksteps; ++kk)  // dK += dS^T Q
-                mma_ts(tmem_base + kAcc1, tmem_base + kColDP + c0 + kk * 8, dq + 128 * kk, idesc_acc, (half | kk) != 0);
-            }
-            if (half == 1 || cB == 0) {
-              mma_commit(bar_accfull);
-              if (ps == npass - 1) mma_commit(&bar_empty[sl]);
-            }
+            const uint32_t idesc = idesc_bf16(128, g.cw, 0, 0);
+            const uint64_t das = smem_desc_sw128(a_s), dap = smem_desc_sw128(a_p);
+            const uint64_t dbs = smem_desc_sw128(b_s + g.c0 * 128), dbp = smem_desc_sw128(b_p + g.c0 * 128);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) mma_ss(T, das + 2 * kk, dbs + 2 * kk, idesc, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) mma_ss(T + g.dp_off, dap + 2 * kk, dbp + 2 * kk, idesc, kk > 0);
+            mma_commit(&bar_sfull[w]);
           }
           __syncwarp();
-          if (lane == 0) dbg_stamp(p, 2, (int)n * 8 + 3 + 2 * half);
+          mbar_wait(&bar_pfull[w], ng & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const int ksteps = g.cw >> 4;
+            const uint32_t adv = (uint32_t)(128 * (g.c0 >> 4));
+            if (is_dq) {
+              const uint64_t dk = smem_desc_sw128(k_b) + adv;
+              for (int kk = 0; kk < ksteps; ++kk)  // dQ += dS K
+                mma_ts(T + 192, T + kk * 8, dk + 128 * kk, idesc_acc, (!first || kk > 0) ? 1u : 0u);
+            } else {
+              const uint64_t dg = smem_desc_sw128(g_b) + adv, dq = smem_desc_sw128(q_b) + adv;
+              for (int kk = 0; kk < ksteps; ++kk)  // dV += P^T dO
+                mma_ts(T + 192, T + kk * 8, dg + 128 * kk, idesc_acc, (!first || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < ksteps; ++kk)  // dK += dS^T Q
+                mma_ts(T + 64, T + g.dp_off + kk * 8, dq + 128 * kk, idesc_acc, (!first || kk > 0) ? 1u : 0u);
+            }
+            if (last) mma_commit(&bar_accfull[w]);
+          }
+          __syncwarp();
+          ++ng;
         }
+        ++nt;
       }
+      // every MMA of this stream that reads the slot has been issued: its retirement releases the slot
+      if (elect_one()) mma_commit(&bar_empty[sl]);
+      __syncwarp();
     }
-  } else if (warp == 10) {
+  } else if (warp == 11) {
     // ============================================ statistics helper =======================================
     // stats[k & 1][i] = (lse_i * log2 e, delta_i = sum_d dO[i][d] O[i][d]) for the rows of item k, one item ahead
     int k = 0;
@@ -321,81 +336,81 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_pl64, const __grid_con
       mbar_arrive(&bar_stfull[sl]);
     }
   } else if (warp < 8) {
-    // ============================================ compute groups ==========================================
+    // ============================================ compute streams =========================================
     const int w = warp >> 2, wq = warp & 3;
     const int lrow = wq * 32 + lane;  // TMEM lane of this thread
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const uint32_t trow = tmem_base + (uint32_t)(w * 256) + ((uint32_t)(wq * 32) << 16);
     const size_t plane = (size_t)BHN * kDh;
-    uint32_t n = 0;
+    const bool dbg_on = p.dbg != nullptr && (tid & 127) == 0;
+    uint32_t ng = 0, nt = 0;
     int k = 0;
     for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++k) {
       const int sl = k & 1;
       const float2* st = stats + sl * 256;
       mbar_wait(&bar_stfull[sl], (uint32_t)((k >> 1) & 1));
-      for (int ps = 0; ps < npass; ++ps, ++n) {
-        const bool is_dq = ps < ntile;
-        const int tile = is_dq ? ps : ps - ntile;
-        const uint32_t par = n & 1;
-        const int half = (w == (int)(n & 1)) ? 0 : 1;  // the big half alternates between the groups
-        const int c0 = half == 0 ? 0 : cA, cw = half == 0 ? cA : cB;
-        const int idx = tile * 128 + lrow;             // query row (dQ pass) / key (dK/dV pass) of this thread
+      for (int lt = 0; lt < 2 * ntile; ++lt) {
+        const bool is_dq = lt < ntile;
+        const int tile = is_dq ? lt : lt - ntile;
+        if (((tile & 1) == w) != is_dq) continue;
+        const int idx = tile * 128 + lrow;             // query row (dQ tile) / key (dKV tile) of this thread
         const bool warp_live = tile * 128 + wq * 32 < N;
-        const bool dbg_on = p.dbg != nullptr && (tid & 127) == 0;
-        if (cw > 0) {
-          if (dbg_on) dbg_stamp(p, w, (int)n * 4 + 0);
-          mbar_wait(&bar_sfull[half], par);
+        const float2 mine = st[min(idx, 255)];
+        const float neg_lse2 = -mine.x, delta = mine.y;
+        const int ngr = num_groups(is_dq, npad);
+#pragma unroll 1
+        for (int gi = 0; gi < ngr; ++gi) {
+          const ColGroup g = group_at(is_dq, npad, gi);
+          if (dbg_on) dbg_stamp(p, w, (int)ng * 4 + 0);
+          mbar_wait(&bar_sfull[w], ng & 1);
           tc_fence_after();
-          if (dbg_on) dbg_stamp(p, w, (int)n * 4 + 1);
+          if (dbg_on) dbg_stamp(p, w, (int)ng * 4 + 1);
           if (warp_live) {
-            const uint32_t t_s = tmem_row + c0, t_dp = tmem_row + kColDP + c0;
-            const int n32 = cw >> 5;
-            if (is_dq) {
-              const float2 mine = st[min(idx, 255)];
-              const float neg_lse2 = -mine.x, delta = mine.y;
-#pragma unroll 1
-              for (int c = 0; c < n32; ++c)
-                dq_chunk<32>(p, t_s + c * 32, t_dp + c * 32, t_s + c * 16, c0 + c * 32, neg_lse2, delta);
-              if (cw & 16) dq_chunk<16>(p, t_s + n32 * 32, t_dp + n32 * 32, t_s + n32 * 16, c0 + n32 * 32, neg_lse2, delta);
-            } else {
-              const float4* st2 = reinterpret_cast<const float4*>(st + c0);
-#pragma unroll 1
-              for (int c = 0; c < n32; ++c)
-                dkv_chunk<32>(p, t_s + c * 32, t_dp + c * 32, t_s + c * 16, t_dp + c * 16, st2 + c * 16);
-              if (cw & 16)
-                dkv_chunk<16>(p, t_s + n32 * 32, t_dp + n32 * 32, t_s + n32 * 16, t_dp + n32 * 16, st2 + n32 * 16);
-            }
+            const float4* st2 = reinterpret_cast<const float4*>(st + g.c0);
+            if (is_dq) process_group<true>(p, trow, trow + g.dp_off, g.cw >> 4, g.c0, neg_lse2, delta, st2);
+            else process_group<false>(p, trow, trow + g.dp_off, g.cw >> 4, g.c0, neg_lse2, delta, st2);
             tmem_wait_st();
           }
           tc_fence_before();
-          mbar_arrive(&bar_pfull[half]);
-          if (dbg_on) dbg_stamp(p, w, (int)n * 4 + 2);
+          mbar_arrive(&bar_pfull[w]);
+          if (dbg_on) dbg_stamp(p, w, (int)ng * 4 + 2);
+          ++ng;
         }
-        // ---- epilogue of the pass ----------------------------------------------------------------------
-        mbar_wait(bar_accfull, par);
+        // ---- epilogue of the lane tile -------------------------------------------------------------------
+        mbar_wait(&bar_accfull[w], nt & 1);
         tc_fence_after();
-        if (dbg_on) dbg_stamp(p, w, (int)n * 4 + 3);
-        uint32_t lo[32], hi[32];
+        if (dbg_on) dbg_stamp(p, w, (int)(ng - 1) * 4 + 3);
         if (warp_live) {
-          if (is_dq) {
-            tmem_ld32(tmem_row + kAcc1 + w * 32, lo);  // group w stores channels [32 w, 32 w + 32) of dQ
-          } else {
-            tmem_ld32(tmem_row + (w == 0 ? kAcc2 : kAcc1), lo);  // group 0: dV, group 1: dK
-            tmem_ld32(tmem_row + (w == 0 ? kAcc2 : kAcc1) + 32, hi);
+          // (ld, arrive, store) in ONE scope: with the loads and the uses in differently-predicated blocks ptxas kept
+          // the 64 accumulator registers in local memory
+          {
+            uint32_t a0[32], a1[32];
+            if (dbg_on && w == 0) dbg_stamp(p, 3, (int)nt * 4 + 0);
+            tmem_ld32(trow + 192, a0);  // dQ or dV
+            tmem_ld32(trow + 224, a1);
+            tmem_wait_ld();
+            if (dbg_on && w == 0) dbg_stamp(p, 3, (int)nt * 4 + 1);
+            if (is_dq) {
+              tc_fence_before();
+              mbar_arrive(&bar_accempty[w]);
+            }
+            if (idx < N) store_row(p.d_planes + (is_dq ? 0 : 2) * plane + ((size_t)bh * N + idx) * kDh, a0, a1, is_dq ? p.scale : 1.f);
+            if (dbg_on && w == 0) dbg_stamp(p, 3, (int)nt * 4 + 2);
           }
-          tmem_wait_ld();
-        }
-        tc_fence_before();
-        mbar_arrive(bar_accempty);
-        if (warp_live && idx < N) {
-          if (is_dq) {
-            store_half_row(p.d_planes + ((size_t)bh * N + idx) * kDh + w * 32, lo, p.scale);
-          } else {
-            __nv_bfloat16* dst = p.d_planes + (w == 0 ? 2 : 1) * plane + ((size_t)bh * N + idx) * kDh;
-            const float mul = w == 0 ? 1.f : p.scale;
-            store_half_row(dst, lo, mul);
-            store_half_row(dst + 32, hi, mul);
+          if (!is_dq) {
+            uint32_t b0[32], b1[32];
+            tmem_ld32(trow + 64, b0);  // dK
+            tmem_ld32(trow + 96, b1);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&bar_accempty[w]);
+            if (idx < N) store_row(p.d_planes + plane + ((size_t)bh * N + idx) * kDh, b0, b1, p.scale);
+            if (dbg_on && w == 0) dbg_stamp(p, 3, (int)nt * 4 + 3);
           }
+        } else {
+          tc_fence_before();
+          mbar_arrive(&bar_accempty[w]);
         }
+        ++nt;
       }
     }
   }

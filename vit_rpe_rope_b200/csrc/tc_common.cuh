@@ -297,6 +297,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_ex(uint32_t smem_addr, uint3
   return d;
 }
 
+// Register re-partitioning between the warpgroups of a CTA (warps 4g .. 4g+3 execute it together): the TMA / MMA
+// issuing warps give registers back, the compute warpgroups take them.  Counts are multiples of 8.
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
