@@ -70,7 +70,13 @@ typedef enum { VRR_BIAS_NONE = 0, VRR_BIAS_TABLE = 1, VRR_BIAS_POLY = 2 } vrr_bi
 typedef enum { VRR_IMPL_AUTO = 0, VRR_IMPL_SIMT = 1, VRR_IMPL_TCGEN05 = 2 } vrr_impl;
 
 /* Epilogues of vrr_gemm_ex (Linear layers, models/vit.py:91,118,285). */
-typedef enum { VRR_EPI_NONE = 0, VRR_EPI_BIAS = 1, VRR_EPI_BIAS_GELU = 2 } vrr_epilogue;
+typedef enum {
+  VRR_EPI_NONE = 0,
+  VRR_EPI_BIAS = 1,            /* c = acc + bias                                                              */
+  VRR_EPI_BIAS_GELU = 2,       /* c = h = acc + bias, c2 = gelu(h)            (exact erf GELU, timm Mlp)        */
+  VRR_EPI_BIAS_GELU_GRAD = 3,  /* c = gelu(h), c2 = d gelu / dh (h)           (what the Mlp backward needs)     */
+  VRR_EPI_MUL = 4              /* c = acc * c2[m][n]; c2 is an INPUT [M][N]   (d_act * gelu'(h) in fc2's dX)    */
+} vrr_epilogue;
 
 typedef struct {
   int32_t mode;        /* vrr_bias_mode                                                  */
@@ -172,7 +178,9 @@ int vrr_gemm(const void* a, const void* b, void* c, int M, int N, int K, int tra
  *   backward dW = dY^T.X           : trans_a 1, trans_b 0, c_dtype VRR_F32
  * epilogue (vrr_epilogue): BIAS adds the fp32 `bias[N]` (cast to `dtype` first, like F.linear on `dtype`
  * tensors) before the single rounding to c_dtype; BIAS_GELU additionally writes C2 = gelu(C), exact erf GELU
- * (timm Mlp, act_layer=nn.GELU).  accumulate != 0 (fp32 C, tcgen05 kernel only): C += result.
+ * (timm Mlp, act_layer=nn.GELU); BIAS_GELU_GRAD writes C = gelu(h) and C2 = gelu'(h) for h = round(acc + bias)
+ * (h itself is not stored: the Mlp backward only needs gelu'); MUL multiplies by the INPUT matrix C2[M][N]
+ * before rounding (fc2's dX fused with the GELU backward: dh = (dy . W2) * gelu'(h)).  accumulate != 0 (fp32 C, tcgen05 kernel only): C += result.
  * bf16 operands with N % 8 == 0, K % 8 == 0 (and M % 8 == 0 when trans_a) and 16-byte aligned pointers run
  * the tcgen05 CTA-pair kernel (cta_group::2, TMA in, TMA store / reduce-add out; fp32 C is split over K and
  * combined by TMA reduce-add, so its summation order is not deterministic); everything else (fp32 operands,

@@ -22,12 +22,12 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def gemm(a, b, ta, tb, c_dtype, bias=None, epi=0, accumulate_into=None):
+def gemm(a, b, ta, tb, c_dtype, bias=None, epi=0, accumulate_into=None, aux=None):
     M = a.shape[1] if ta else a.shape[0]
     K = a.shape[0] if ta else a.shape[1]
     N = b.shape[0] if tb else b.shape[1]
     c = accumulate_into if accumulate_into is not None else torch.empty(M, N, device=dev, dtype=c_dtype)
-    c2 = torch.empty_like(c) if epi == 2 else None
+    c2 = torch.empty_like(c) if epi in (2, 3) else (aux if epi == 4 else None)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     rc = lib.vrr_gemm_ex(ptr(a), ptr(b), ptr(c), ptr(c2), ptr(bias), M, N, K, ta, tb, 1, 0 if c_dtype == torch.float32 else 1,
                          epi, 1 if accumulate_into is not None else 0, st)
@@ -72,9 +72,23 @@ if which == "check":
                 e3 = rel(a2, torch.nn.functional.gelu(h.float()))
                 cf, _ = gemm(a, b, ta, tb, torch.float32, bias, 1)
                 e4 = rel(cf, want + bias)
-                ok = e1 <= 8e-3 and e2 <= 8e-3 and e3 <= 8e-3 and e4 <= 2e-5
+                a3, gp = gemm(a, b, ta, tb, torch.bfloat16, bias, 3)
+                torch.cuda.synchronize()
+                hf = h.float().requires_grad_(True)
+                torch.nn.functional.gelu(hf).sum().backward()
+                e5, e6 = rel(a3, torch.nn.functional.gelu(h.float())), rel(gp, hf.grad)
+                ok = e1 <= 8e-3 and e2 <= 8e-3 and e3 <= 8e-3 and e4 <= 2e-5 and e5 <= 8e-3 and e6 <= 8e-3
                 bad += not ok
-                print(f"     bias {e1:.2e}  bias+gelu h {e2:.2e} gelu {e3:.2e}  fp32+bias {e4:.2e} {'ok' if ok else 'BAD'}", flush=True)
+                print(f"     bias {e1:.2e}  bias+gelu h {e2:.2e} gelu {e3:.2e}  fp32+bias {e4:.2e}  gelu/grad {e5:.2e} {e6:.2e} "
+                      f"{'ok' if ok else 'BAD'}", flush=True)
+            if (ta, tb) == (0, 0) and N % 8 == 0:
+                mul = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
+                c, _ = gemm(a, b, ta, tb, torch.bfloat16, None, 4, aux=mul)
+                torch.cuda.synchronize()
+                e = rel(c, want * mul.float())
+                ok = e <= 8e-3
+                bad += not ok
+                print(f"     mul epilogue: {e:.2e} {'ok' if ok else 'BAD'}", flush=True)
             if (ta, tb) == (1, 0):
                 acc = torch.randn(M, N, generator=g).to(dev)
                 base = acc.clone()
@@ -107,7 +121,8 @@ if which == "time":
     for geo, E in (("vitb", 768), ("vitl", 1024)):
         Mtok = rows[geo]
         cases = [("qkv fwd  NT", Mtok, 3 * E, E, 0, 1, torch.bfloat16, 0), ("proj fwd NT", Mtok, E, E, 0, 1, torch.bfloat16, 1),
-                 ("fc1 fwd  NT+gelu", Mtok, 4 * E, E, 0, 1, torch.bfloat16, 2), ("fc2 fwd  NT", Mtok, E, 4 * E, 0, 1, torch.bfloat16, 1),
+                 ("fc1 fwd  NT+gelu", Mtok, 4 * E, E, 0, 1, torch.bfloat16, 2), ("fc1 fwd  NT+gelu+grad", Mtok, 4 * E, E, 0, 1, torch.bfloat16, 3),
+                 ("fc2 dX   NN*mul", Mtok, 4 * E, E, 0, 0, torch.bfloat16, 4), ("fc2 fwd  NT", Mtok, E, 4 * E, 0, 1, torch.bfloat16, 1),
                  ("qkv dX   NN", Mtok, E, 3 * E, 0, 0, torch.bfloat16, 0), ("fc1 dX   NN", Mtok, E, 4 * E, 0, 0, torch.bfloat16, 0),
                  ("fc2 dX   NN", Mtok, 4 * E, E, 0, 0, torch.bfloat16, 0),
                  ("qkv dW   TN", 3 * E, E, Mtok, 1, 0, torch.float32, 0), ("proj dW  TN", E, E, Mtok, 1, 0, torch.float32, 0),
@@ -115,8 +130,9 @@ if which == "time":
         for name, M, N, K, ta, tb, cdt, epi in cases:
             a = (torch.randn((K, M) if ta else (M, K), generator=g) * 0.5).to(torch.bfloat16).to(dev)
             b = (torch.randn((N, K) if tb else (K, N), generator=g) * 0.5).to(torch.bfloat16).to(dev)
-            bias = torch.randn(N, generator=g).to(dev) if epi else None
-            t_mine = timeit(lambda: gemm(a, b, ta, tb, cdt, bias, epi))
+            bias = torch.randn(N, generator=g).to(dev) if epi in (1, 2, 3) else None
+            aux = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev) if epi == 4 else None
+            t_mine = timeit(lambda: gemm(a, b, ta, tb, cdt, bias, epi, aux=aux))
             aa, bb = (a.t() if ta else a), (b.t() if tb else b)
             t_lib = timeit(lambda: torch.matmul(aa, bb))
             fl = 2.0 * M * N * K

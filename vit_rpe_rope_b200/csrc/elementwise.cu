@@ -99,7 +99,35 @@ __global__ void __launch_bounds__(kCsThreads) gelu_bwd_colsum_kernel(const T* __
   }
 }
 
+// SIMT-family fallbacks of the GEMM epilogues VRR_EPI_BIAS_GELU_GRAD / VRR_EPI_MUL (fp32, odd shapes, forced SIMT)
+template <typename T>
+__global__ void gelu_grad_inplace_kernel(T* __restrict__ h, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    Elem<T>::st(h + i, gelu_grad(Elem<T>::ld(h + i)));
+}
+template <typename T>
+__global__ void mul_inplace_kernel(T* __restrict__ c, const T* __restrict__ m, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    Elem<T>::st(c + i, Elem<T>::ld(c + i) * Elem<T>::ld(m + i));
+}
+
 }  // namespace
+
+int gelu_grad_inplace(void* h, size_t n, int dtype, cudaStream_t st) {
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (dtype == VRR_F32) gelu_grad_inplace_kernel<float><<<grid, 256, 0, st>>>((float*)h, n);
+  else gelu_grad_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)h, n);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
+int mul_inplace(void* c, const void* m, size_t n, int dtype, cudaStream_t st) {
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (dtype == VRR_F32) mul_inplace_kernel<float><<<grid, 256, 0, st>>>((float*)c, (const float*)m, n);
+  else mul_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)c, (const __nv_bfloat16*)m, n);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
 
 int colsum(const void* x, float* out, int M, int C, int dtype, cudaStream_t st) {
   VRR_REQUIRE(C % 4 == 0, VRR_ERR_UNSUPPORTED, "colsum: C = %d must be a multiple of 4", C);

@@ -123,23 +123,40 @@ struct StoreEpi {
   const float* bias;  // fp32 [N] or null; rounded to bf16 first when C is bf16 (autocast casts the bias)
   int out_f32;        // C element type: 0 bf16, 1 fp32
   int reduce;         // fp32 only: C += tile via TMA reduce-add (split-K partial sums / gradient accumulation)
-  int gelu;           // bf16 only: C = h = bf16(acc + bias), C2 = bf16(gelu(h)) (exact erf GELU)
+  int gelu;           // bf16 only.  1: C = h = bf16(acc + bias), C2 = bf16(gelu(h)) (exact erf GELU);
+                      //            2: C = bf16(gelu(h)), C2 = bf16(gelu'(h)) - what an Mlp backward needs instead of h
+  const __nv_bfloat16* mul;  // bf16 only, or null: C = bf16(acc * mul[m][n]) (mul is [M][N] like C): d_act * gelu'(h)
 };
 
-// exact GELU 0.5 x (1 + erf(x / sqrt 2)); erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7)
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erf_abs = 1.f - poly * ex2(-z * z * 1.4426950408889634f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.f + erf_v);
+// gelu(h) and d gelu / dh for TWO values at a time on the packed fp32x2 pipe (fma.rn.f32x2, sm_100): the epilogue of
+// fc1 is bound by its instruction count (128 x 256 outputs per CTA against ~6 100 tensor-clocks of MMA per tile), and
+// the scalar version (~20 FMA-pipe ops per element) made the GEMM run at half the speed of the plain one.
+//   Phi(h) = 1 - erfc(|h| / sqrt 2) / 2 (h >= 0), erfc / 2 otherwise; erfc(z) = (a1 t + .. + a5 t^5) exp(-z^2),
+//   t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7); gelu = h Phi, gelu' = Phi + h phi(h) with
+//   phi(h) = exp(-h^2 / 2) / sqrt(2 pi) - the same exponential.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-
+__device__ __forceinline__ void gelu_and_grad2(float2 h, float2& g, float2& dg) {
+  const float2 hh = __fmul2_rn(h, h);
+  const float2 ea = __fmul2_rn(hh, make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  const float2 e = make_float2(ex2(ea.x), ex2(ea.y));  // exp(-h^2 / 2)
+  const float2 za = make_float2(fabsf(h.x), fabsf(h.y));
+  const float2 den = __ffma2_rn(za, make_float2(0.23164190f, 0.23164190f), make_float2(1.f, 1.f));  // 1 + p |h| / sqrt 2
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  // coefficients pre-multiplied by 1/2
+  float2 poly = __ffma2_rn(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+  poly = __ffma2_rn(poly, t, make_float2(0.7107068705f, 0.7107068705f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.142248368f, -0.142248368f));
+  poly = __ffma2_rn(poly, t, make_float2(0.127414796f, 0.127414796f));
+  const float2 q = __fmul2_rn(__fmul2_rn(poly, t), e);  // erfc(|h| / sqrt 2) / 2
+  const float2 om = __ffma2_rn(q, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  const float2 cdf = make_float2(h.x >= 0.f ? om.x : q.x, h.y >= 0.f ? om.y : q.y);  // Phi(h)
+  g = __fmul2_rn(h, cdf);
+  dg = __ffma2_rn(__fmul2_rn(h, e), make_float2(0.3989422804014327f, 0.3989422804014327f), cdf);
+}
 
 // ---------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -274,6 +291,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         uint32_t v[64];
+        [[maybe_unused]] uint4 mv[8];  // StoreEpi::mul: this thread's 64 multipliers, in flight behind the TMEM load
+        if constexpr (Epi::kTma) {
+          if (epi.mul != nullptr) {
+            const int n0m = n_blk * BN + chalf * (BN / 2) + c * 64;
+            const int mr = m < g.M ? m : g.M - 1;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const int nb = max(min(n0m + c8 * 8, g.N - 8), 0);
+              mv[c8] = __ldg(reinterpret_cast<const uint4*>(epi.mul + (size_t)mr * g.N + nb));
+            }
+          }
+        }
         __syncwarp();  // tcgen05.ld is .sync.aligned
         tmem_ld32(trow + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld32(trow + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -292,49 +321,86 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t sw = (uint32_t)(lane & 7);
           const uint32_t row_base = stage_u32 + (uint32_t)lane * 128u;
           if (!epi.out_f32) {
-            // ---- bf16 C (optionally + C2 = gelu) ----
-            const bool two = epi.gelu != 0;
-            const uint32_t buf = two ? 0u : (chunk_counter & 1u) * 4096u;
-            if (lane == 0) {
-              if (two) bulk_wait_read<0>(); else bulk_wait_read<1>();
-            }
-            __syncwarp();
+            // ---- bf16 C ----
+            if (epi.gelu != 0) {
+              // two outputs: (h, gelu(h)) or (gelu(h), gelu'(h)).  The chunk is computed into registers FIRST and only
+              // then waits for the previous chunk's TMA stores to release the two staging buffers.
+              uint32_t o0[32], o1[32];
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-              float x[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] = f[c8 * 8 + j];
-              if (epi.bias != nullptr) {
+              for (int c8 = 0; c8 < 8; ++c8) {
                 const int nb = min(n0 + c8 * 8, g.N - 8);  // N % 8 == 0; clamp keeps the tail read in bounds
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb));
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb + 4));
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] += __bfloat162float(__float2bfloat16_rn(bb[j]));
-              }
-              const uint32_t w0 = pack_bf16(x[0], x[1]), w1 = pack_bf16(x[2], x[3]);
-              const uint32_t w2 = pack_bf16(x[4], x[5]), w3 = pack_bf16(x[6], x[7]);
-              const uint32_t off = (((uint32_t)c8 ^ sw) << 4);
-              st_shared_v4(row_base + buf + off, w0, w1, w2, w3);
-              if (two) {
-                const uint32_t ws[4] = {w0, w1, w2, w3};
-                uint32_t gs[4];
+                const uint32_t br[4] = {pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w)};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float2 h2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ws[j]));
-                  gs[j] = pack_bf16(gelu_erf(h2.x), gelu_erf(h2.y));
+                  const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&br[j]));  // bias as bf16
+                  const float2 hs = __fadd2_rn(make_float2(f[c8 * 8 + 2 * j], f[c8 * 8 + 2 * j + 1]), bb);
+                  const uint32_t hw = pack_bf16(hs.x, hs.y);
+                  const float2 hr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));  // h as stored
+                  float2 gl, dg;
+                  gelu_and_grad2(hr, gl, dg);
+                  if (epi.gelu == 1) {
+                    o0[c8 * 4 + j] = hw;
+                    o1[c8 * 4 + j] = pack_bf16(gl.x, gl.y);
+                  } else {
+                    o0[c8 * 4 + j] = pack_bf16(gl.x, gl.y);
+                    o1[c8 * 4 + j] = pack_bf16(dg.x, dg.y);
+                  }
                 }
-                st_shared_v4(row_base + 4096u + off, gs[0], gs[1], gs[2], gs[3]);
               }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (store_ok) {
-                tma_store_2d(&tmap_c, my_stage + buf, n0, m_warp0);
-                if (two) tma_store_2d(&tmap_c2, my_stage + 4096, n0, m_warp0);
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                const uint32_t off = (((uint32_t)c8 ^ sw) << 4);
+                st_shared_v4(row_base + off, o0[c8 * 4], o0[c8 * 4 + 1], o0[c8 * 4 + 2], o0[c8 * 4 + 3]);
+                st_shared_v4(row_base + 4096u + off, o1[c8 * 4], o1[c8 * 4 + 1], o1[c8 * 4 + 2], o1[c8 * 4 + 3]);
               }
-              bulk_commit();
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (store_ok) {
+                  tma_store_2d(&tmap_c, my_stage, n0, m_warp0);
+                  tma_store_2d(&tmap_c2, my_stage + 4096, n0, m_warp0);
+                }
+                bulk_commit();
+              }
+            } else {
+              const uint32_t buf = (chunk_counter & 1u) * 4096u;
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = f[c8 * 8 + j];
+                if (epi.bias != nullptr) {
+                  const int nb = min(n0 + c8 * 8, g.N - 8);
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb + 4));
+                  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) x[j] += __bfloat162float(__float2bfloat16_rn(bb[j]));
+                }
+                if (epi.mul != nullptr) {
+                  const uint32_t mw[4] = {mv[c8].x, mv[c8].y, mv[c8].z, mv[c8].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 m2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mw[j]));
+                    x[2 * j] *= m2.x;
+                    x[2 * j + 1] *= m2.y;
+                  }
+                }
+                st_shared_v4(row_base + buf + (((uint32_t)c8 ^ sw) << 4), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                             pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (store_ok) tma_store_2d(&tmap_c, my_stage + buf, n0, m_warp0);
+                bulk_commit();
+              }
             }
           } else {
             // ---- fp32 C: two [32 rows][32 floats] boxes per 64-column chunk ----
@@ -450,9 +516,11 @@ template <bool A_MN, bool B_MN>
 int launch_store(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int c_f32,
                  int epilogue, int accumulate, cudaStream_t st) {
   StoreEpi epi;
-  epi.bias = epilogue != VRR_EPI_NONE ? bias : nullptr;
+  epi.bias = (epilogue != VRR_EPI_NONE && epilogue != VRR_EPI_MUL) ? bias : nullptr;
   epi.out_f32 = c_f32;
-  epi.gelu = epilogue == VRR_EPI_BIAS_GELU;
+  epi.gelu = epilogue == VRR_EPI_BIAS_GELU ? 1 : (epilogue == VRR_EPI_BIAS_GELU_GRAD ? 2 : 0);
+  epi.mul = epilogue == VRR_EPI_MUL ? (const __nv_bfloat16*)c2 : nullptr;
+  if (epilogue == VRR_EPI_MUL) epi.bias = nullptr;
   const int tiles = ceil_div(M, 2 * kPM) * ceil_div(N, N > 128 ? 256 : 128);
   int splits = 1;
   if (c_f32) splits = pick_splits(tiles, ceil_div(K, kPK), sm_count() / 2);
@@ -487,8 +555,8 @@ bool gemm_bf16_tc_supported(int M, int N, int K, int trans_a, int trans_b, int c
   if ((trans_b ? K : N) % 8 != 0) return false;   // B stored [N][K] or [K][N]
   if (c_dtype == VRR_BF16 ? (N % 8 != 0) : (N % 4 != 0)) return false;
   if (c_dtype != VRR_F32 && c_dtype != VRR_BF16) return false;
-  if (epilogue == VRR_EPI_BIAS_GELU && c_dtype != VRR_BF16) return false;
-  if (epilogue != VRR_EPI_NONE && N % 8 != 0) return false;  // vector loads of the bias
+  if (epilogue >= VRR_EPI_BIAS_GELU && c_dtype != VRR_BF16) return false;
+  if (epilogue != VRR_EPI_NONE && N % 8 != 0) return false;  // vector loads of the bias / the multiplier
   if ((long long)M * N >= (1ll << 40)) return false;
   return true;
 }
@@ -497,9 +565,10 @@ int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* b
                  int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st) {
   VRR_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)c2) & 15) == 0, VRR_ERR_INVALID_ARG,
               "gemm (tcgen05): a / b / c must be 16-byte aligned");
-  VRR_REQUIRE(epilogue == VRR_EPI_NONE || (bias != nullptr && ((uintptr_t)bias & 15) == 0), VRR_ERR_INVALID_ARG,
-              "gemm (tcgen05): the bias epilogues need a 16-byte aligned fp32 bias");
-  VRR_REQUIRE(epilogue != VRR_EPI_BIAS_GELU || c2 != nullptr, VRR_ERR_INVALID_ARG, "gemm (tcgen05): BIAS_GELU needs c2");
+  VRR_REQUIRE(epilogue == VRR_EPI_NONE || epilogue == VRR_EPI_MUL || (bias != nullptr && ((uintptr_t)bias & 15) == 0),
+              VRR_ERR_INVALID_ARG, "gemm (tcgen05): the bias epilogues need a 16-byte aligned fp32 bias");
+  VRR_REQUIRE(epilogue < VRR_EPI_BIAS_GELU || c2 != nullptr, VRR_ERR_INVALID_ARG,
+              "gemm (tcgen05): the GELU / MUL epilogues need c2");
   VRR_REQUIRE(!accumulate || c_dtype == VRR_F32, VRR_ERR_UNSUPPORTED, "gemm (tcgen05): accumulate needs an fp32 C");
   const int c_f32 = c_dtype == VRR_F32;
   const bool a_mn = trans_a != 0, b_mn = trans_b == 0;

@@ -99,6 +99,8 @@ int add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, con
 // elementwise.cu
 int colsum(const void* x, float* out, int M, int C, int dtype, cudaStream_t st);
 int gelu_bwd_colsum(const void* dy, const void* h, void* dh, float* db, int M, int C, int dtype, cudaStream_t st);
+int gelu_grad_inplace(void* h, size_t n, int dtype, cudaStream_t st);            // h <- d gelu / dh (h)
+int mul_inplace(void* c, const void* m, size_t n, int dtype, cudaStream_t st);  // c <- c * m
 
 // rope.cu
 int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab, const float* sin_tab,

@@ -291,9 +291,10 @@ int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bi
   VRR_REQUIRE(a && b && c, VRR_ERR_INVALID_ARG, "gemm_ex: NULL pointer");
   VRR_REQUIRE(M > 0 && N > 0 && K > 0, VRR_ERR_INVALID_ARG, "gemm_ex: bad sizes");
   VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(c_dtype), VRR_ERR_INVALID_ARG, "gemm_ex: bad dtype %d/%d", dtype, c_dtype);
-  VRR_REQUIRE(epilogue >= VRR_EPI_NONE && epilogue <= VRR_EPI_BIAS_GELU, VRR_ERR_INVALID_ARG, "gemm_ex: bad epilogue %d", epilogue);
-  VRR_REQUIRE(epilogue == VRR_EPI_NONE || bias, VRR_ERR_INVALID_ARG, "gemm_ex: the bias epilogues need `bias`");
-  VRR_REQUIRE(epilogue != VRR_EPI_BIAS_GELU || c2, VRR_ERR_INVALID_ARG, "gemm_ex: BIAS_GELU needs `c2`");
+  VRR_REQUIRE(epilogue >= VRR_EPI_NONE && epilogue <= VRR_EPI_MUL, VRR_ERR_INVALID_ARG, "gemm_ex: bad epilogue %d", epilogue);
+  VRR_REQUIRE(epilogue == VRR_EPI_NONE || epilogue == VRR_EPI_MUL || bias, VRR_ERR_INVALID_ARG,
+              "gemm_ex: the bias epilogues need `bias`");
+  VRR_REQUIRE(epilogue < VRR_EPI_BIAS_GELU || c2, VRR_ERR_INVALID_ARG, "gemm_ex: the GELU / MUL epilogues need `c2`");
   if (int rc = require_device()) return rc;
   const int impl = g_impl.load();
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && gemm_bf16_tc_supported(M, N, K, trans_a, trans_b, c_dtype, epilogue)) {
@@ -305,8 +306,17 @@ int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bi
               "(M %% 8 == 0 when trans_a)", M, N, K, trans_a, trans_b);
   VRR_REQUIRE(!accumulate, VRR_ERR_UNSUPPORTED, "gemm_ex: accumulate is implemented by the tcgen05 kernel only");
   VRR_COUNT_FAMILY(VRR_IMPL_SIMT);
+  if (epilogue == VRR_EPI_MUL) {
+    VRR_REQUIRE(c_dtype == dtype, VRR_ERR_UNSUPPORTED, "gemm_ex (SIMT): the MUL epilogue needs c_dtype == dtype");
+    if (int rc = gemm_simt(a, b, c, M, N, K, trans_a, trans_b, dtype, c_dtype, (cudaStream_t)stream)) return rc;
+    return mul_inplace(c, c2, (size_t)M * N, c_dtype, (cudaStream_t)stream);
+  }
   if (epilogue != VRR_EPI_NONE) {
     VRR_REQUIRE(c_dtype == dtype, VRR_ERR_UNSUPPORTED, "gemm_ex (SIMT): the bias epilogues need c_dtype == dtype");
+    if (epilogue == VRR_EPI_BIAS_GELU_GRAD) {  // (h, gelu(h)) into (c2, c), then c2 <- gelu'(h)
+      if (int rc = gemm_simt_bias(a, b, c2, c, bias, M, N, K, trans_a, trans_b, dtype, 1, (cudaStream_t)stream)) return rc;
+      return gelu_grad_inplace(c2, (size_t)M * N, dtype, (cudaStream_t)stream);
+    }
     return gemm_simt_bias(a, b, c, c2, bias, M, N, K, trans_a, trans_b, dtype, epilogue == VRR_EPI_BIAS_GELU,
                           (cudaStream_t)stream);
   }

@@ -264,21 +264,22 @@ class QkvRopeFn(torch.autograd.Function):
         return dx, dw, d_cos, d_sin, None, None
 
 
-def _gemm(a, b, trans_a, trans_b, out_dtype, bias=None, epilogue=_lib.EPI_NONE, out2=False, name="gemm"):
+def _gemm(a, b, trans_a, trans_b, out_dtype, bias=None, epilogue=_lib.EPI_NONE, out2=False, name="gemm", aux=None):
     """C = op(A) . op(B) in the library's kernels (``vrr_gemm_ex``) - no cuBLAS anywhere on the path.
 
     op(A) is [M][K] (trans_a: A stored [K][M]); op(B) is [K][N] (trans_b: B stored [N][K]).  bf16 operands
     run the tcgen05 CTA-pair kernel (fp32 accumulation; result in ``out_dtype``: bf16, or fp32 for weight
     gradients), fp32 operands the exact-fp32 FFMA kernel (no TF32).  ``epilogue``: fused ``+ bias`` or
-    ``+ bias, GELU`` (``out2``: also return gelu(C))."""
+    ``+ bias, GELU`` (``out2``: second output - gelu(C) for EPI_BIAS_GELU; EPI_BIAS_GELU_GRAD returns
+    (gelu(h), gelu'(h)) instead); ``aux``: the [M][N] multiplier of EPI_MUL."""
     lib = _lib.load()
     M = a.shape[1] if trans_a else a.shape[0]
     K = a.shape[0] if trans_a else a.shape[1]
     N = b.shape[0] if trans_b else b.shape[1]
     a, b = a.contiguous(), b.contiguous()
     c = torch.empty(M, N, device=a.device, dtype=out_dtype)
-    c2 = torch.empty_like(c) if out2 else None
-    bias32 = _f32c(bias) if epilogue != _lib.EPI_NONE else None
+    c2 = torch.empty_like(c) if out2 else (aux.contiguous() if aux is not None else None)
+    bias32 = _f32c(bias) if bias is not None and epilogue != _lib.EPI_NONE else None
     with _timed(name):
         _lib.check(lib.vrr_gemm_ex(_ptr(a), _ptr(b), _ptr(c), _ptr(c2), _ptr(bias32), M, N, K, int(trans_a), int(trans_b),
                                    _DT[a.dtype], _DT[out_dtype], int(epilogue), 0, _stream()), "vrr_gemm_ex")
@@ -521,9 +522,10 @@ class LinearFn(torch.autograd.Function):
 
 
 class MlpFn(torch.autograd.Function):
-    """fc1 -> exact GELU -> fc2 (timm Mlp, models/vit.py:118).  bf16: fc1 with bias + GELU fused in the GEMM
-    epilogue (h and gelu(h) both written: the backward needs h), fc2 with its bias; backward = four GEMMs on the
-    same kernel (dW in fp32) + gelu' fused with the fc1 bias-gradient reduction + one column sum."""
+    """fc1 -> exact GELU -> fc2 (timm Mlp, models/vit.py:118).  fc1's GEMM epilogue adds the bias and writes BOTH
+    gelu(h) and gelu'(h) (h itself is never stored: the backward only needs the derivative); fc2 adds its bias.
+    Backward = four GEMMs on the same kernel (dW in fp32); the GELU backward is the epilogue of fc2's dX GEMM
+    (dh = (dy . W2) * gelu'(h)), the two bias gradients are column sums."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w1_lp=None, w2_lp=None):
@@ -532,34 +534,28 @@ class MlpFn(torch.autograd.Function):
         w1l = (w1_lp if w1_lp is not None else w1.detach().to(dt)).detach()
         w2l = (w2_lp if w2_lp is not None else w2.detach().to(dt)).detach()
         x2 = x.reshape(-1, x.shape[-1])
-        h, a = _gemm(x2, w1l, False, True, dt, bias=b1, epilogue=_lib.EPI_BIAS_GELU, out2=True, name="fc1_fwd")
+        a, gp = _gemm(x2, w1l, False, True, dt, bias=b1, epilogue=_lib.EPI_BIAS_GELU_GRAD, out2=True, name="fc1_fwd")
         y = _gemm(a, w2l, False, True, dt, bias=b2, epilogue=_lib.EPI_BIAS, name="fc2_fwd")
-        ctx.save_for_backward(x2, h, a, w1l, w2l)
+        ctx.save_for_backward(x2, gp, a, w1l, w2l)
         ctx.meta = (x.shape, w1.dtype, b1.dtype, w2.dtype, b2.dtype)
         return y.view(*x.shape[:-1], w2l.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        lib = _lib.load()
-        x2, h2, a2, w1l, w2l = ctx.saved_tensors
+        x2, gp, a2, w1l, w2l = ctx.saved_tensors
         x_shape, w1_dt, b1_dt, w2_dt, b2_dt = ctx.meta
         dy2 = dy.contiguous().view(-1, dy.shape[-1])
         if dy2.dtype != x2.dtype:
             dy2 = dy2.to(x2.dtype)
-        M, C = h2.shape
         with torch.cuda.device(dy.device):
-            da = _gemm(dy2, w2l, False, False, x2.dtype, name="fc2_dx")
+            dh = _gemm(dy2, w2l, False, False, x2.dtype, epilogue=_lib.EPI_MUL, aux=gp, name="fc2_dx")
             dw2 = _gemm(dy2, a2, True, False, w2_dt, name="fc2_dw")
             with _timed("colsum"):
                 db2 = _colsum(dy2).to(b2_dt)
-            dh = torch.empty_like(h2)
-            db1 = torch.empty(C, device=dy.device, dtype=torch.float32)
-            with _timed("gelu_bwd"):
-                _lib.check(lib.vrr_gelu_bwd(_ptr(da), _ptr(h2), _ptr(dh), _ptr(db1), M, C, _DT[h2.dtype], _stream()),
-                           "vrr_gelu_bwd")
+                db1 = _colsum(dh).to(b1_dt)  # sums the values as stored (rounded), like autograd's sum over dh
             dx = _gemm(dh, w1l, False, False, x2.dtype, name="fc1_dx").view(x_shape)
             dw1 = _gemm(dh, x2, True, False, w1_dt, name="fc1_dw")
-        return dx, dw1, db1.to(b1_dt), dw2, db2, None, None
+        return dx, dw1, db1, dw2, db2, None, None
 
 
 def linear(x, lin: torch.nn.Linear, w_lp=None):
