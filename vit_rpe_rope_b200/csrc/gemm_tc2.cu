@@ -48,16 +48,22 @@ struct PairShape {
 // ---------------------------------------------------------------------------------------------------
 // Epilogues.  kTma = false: functor called per (row, 64-column chunk) with the fp32 accumulators.
 // ---------------------------------------------------------------------------------------------------
+// kPlaneStore: the functor only transforms the 64 accumulators of (row m, head chunk n0) in registers; the kernel
+// rounds them to bf16, stages 32 rows x 128 B per warp in swizzled shared memory and writes them with TMA through a
+// 3-D map of planes[3 B H][N][64]; the one warp tile in N / 32 that runs into the next image falls back to per-thread
+// row stores.  A thread writing its own 128-byte row touched 32 lines per store instruction and made
+// this GEMM 1.7x slower than the plain one.
 struct QkvRopeEpi2 {
   static constexpr bool kTma = false;
+  static constexpr bool kPlaneStore = true;
   __nv_bfloat16* planes;
   const float *cos_tab, *sin_tab;
   int B, N, E, H, rope_mode;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&f)[64]) const {
+  __device__ __forceinline__ void rotate(int m, int n0, float (&f)[64]) const {
     const int hd = 32;
     const int b = m / N, t = m - b * N;
     const int which = n0 / E, h = (n0 - which * E) >> 6;
-    if (rope_mode != VRR_ROPE_NONE && which < 2 && t >= 1) {
+    if (rope_mode != VRR_ROPE_NONE && which < 2 && t >= 1 && b < B) {
       const size_t base = ((size_t)(rope_mode == VRR_ROPE_MIXED ? h * (N - 1) : 0) + (t - 1)) * hd;
       const float4* c4 = reinterpret_cast<const float4*>(cos_tab + base);
       const float4* s4 = reinterpret_cast<const float4*>(sin_tab + base);
@@ -74,16 +80,11 @@ struct QkvRopeEpi2 {
         }
       }
     }
-    __nv_bfloat16* dst = planes + ((((size_t)which * B + b) * H + h) * N + t) * 64;
-#pragma unroll
-    for (int v8 = 0; v8 < 8; ++v8) {
-      uint4 w;
-      w.x = pack_bf16(f[v8 * 8 + 0], f[v8 * 8 + 1]);
-      w.y = pack_bf16(f[v8 * 8 + 2], f[v8 * 8 + 3]);
-      w.z = pack_bf16(f[v8 * 8 + 4], f[v8 * 8 + 5]);
-      w.w = pack_bf16(f[v8 * 8 + 6], f[v8 * 8 + 7]);
-      *reinterpret_cast<uint4*>(dst + v8 * 8) = w;
-    }
+  }
+  // plane index (third map coordinate) of the head chunk n0 for image b
+  __device__ __forceinline__ int plane_of(int b, int n0) const {
+    const int which = n0 / E, h = (n0 - which * E) >> 6;
+    return (which * B + b) * H + h;
   }
 };
 
@@ -91,6 +92,7 @@ struct QkvRopeEpi2 {
 template <typename TT>
 struct PatchEmbedEpi2 {
   static constexpr bool kTma = false;
+  static constexpr bool kPlaneStore = false;
   TT* tokens;
   const __nv_bfloat16* bias;
   const TT* pos;  // may be null
@@ -120,6 +122,7 @@ struct PatchEmbedEpi2 {
 // template instances small.
 struct StoreEpi {
   static constexpr bool kTma = true;
+  static constexpr bool kPlaneStore = false;
   const float* bias;  // fp32 [N] or null; rounded to bf16 first when C is bf16 (autocast casts the bias)
   int out_f32;        // C element type: 0 bf16, 1 fp32
   int reduce;         // fp32 only: C += tile via TMA reduce-add (split-K partial sums / gradient accumulation)
@@ -314,7 +317,45 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const int n0 = n_blk * BN + chalf * (BN / 2) + c * 64;
         float(&f)[64] = *reinterpret_cast<float(*)[64]>(v);
-        if constexpr (!Epi::kTma) {
+        if constexpr (Epi::kPlaneStore) {
+          epi.rotate(m, n0, f);
+          const int b0 = m_warp0 / epi.N, t0 = m_warp0 - b0 * epi.N;
+          const bool in_range = n0 < g.N && m_warp0 < g.M;
+          if (t0 + 32 <= epi.N || !in_range) {
+            // the warp's 32 rows lie in one image: swizzled staging + one TMA store
+            const uint32_t buf = (chunk_counter & 1u) * 4096u;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const uint32_t sw = (uint32_t)(lane & 7);
+            const uint32_t row_base = stage_u32 + buf + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8)
+              st_shared_v4(row_base + (((uint32_t)c8 ^ sw) << 4), pack_bf16(f[c8 * 8 + 0], f[c8 * 8 + 1]),
+                           pack_bf16(f[c8 * 8 + 2], f[c8 * 8 + 3]), pack_bf16(f[c8 * 8 + 4], f[c8 * 8 + 5]),
+                           pack_bf16(f[c8 * 8 + 6], f[c8 * 8 + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (in_range) tma_store_3d(&tmap_c, my_stage + buf, 0, t0, epi.plane_of(b0, n0));
+              bulk_commit();
+            }
+            ++chunk_counter;
+          } else if (m < g.M) {
+            // the rows run into the next image (one warp tile in N / 32; TMA stores take no negative coordinates -
+            // "illegal instruction" - and a box cannot be shortened): each thread stores its own row
+            const int b = m / epi.N, t = m - b * epi.N;
+            __nv_bfloat16* dst = epi.planes + ((size_t)epi.plane_of(b, n0) * epi.N + t) * 64;
+#pragma unroll
+            for (int v8 = 0; v8 < 8; ++v8) {
+              uint4 wv;
+              wv.x = pack_bf16(f[v8 * 8 + 0], f[v8 * 8 + 1]);
+              wv.y = pack_bf16(f[v8 * 8 + 2], f[v8 * 8 + 3]);
+              wv.z = pack_bf16(f[v8 * 8 + 4], f[v8 * 8 + 5]);
+              wv.w = pack_bf16(f[v8 * 8 + 6], f[v8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(dst + v8 * 8) = wv;
+            }
+          }
+        } else if constexpr (!Epi::kTma) {
           if (m < g.M && n0 < g.N) epi(m, n0, f);
         } else {
           const bool store_ok = (n0 < g.N) && (m_warp0 < g.M);
@@ -442,7 +483,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if constexpr (Epi::kTma) {
+    if constexpr (Epi::kTma || Epi::kPlaneStore) {
       if (lane == 0) bulk_wait<0>();  // all stores of this warp have been written
     }
   }
@@ -587,11 +628,11 @@ int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const f
     VRR_REQUIRE(((uintptr_t)cos_tab & 15) == 0 && ((uintptr_t)sin_tab & 15) == 0, VRR_ERR_INVALID_ARG,
                 "qkv_rope_fwd (tcgen05): cos / sin must be 16-byte aligned");
   QkvRopeEpi2 epi{(__nv_bfloat16*)planes, cos_tab, sin_tab, B, N, E, H, rope_mode};
-  CUtensorMap dummy;
-  memset(&dummy, 0, sizeof(dummy));
+  CUtensorMap tplanes;  // planes[3 B H][N][64] bf16, box = [1][32 rows][64]
+  if (int rc = make_tmap_3d_bf16(&tplanes, planes, 64, (uint64_t)N, (uint64_t)3 * B * H, 128, (uint64_t)N * 128, 64, 32)) return rc;
   // 64-column chunks are whole heads (3E = 192 H); a ragged last n-tile is clipped by the n0 < N test
-  if (3 * E > 128) return launch_pair<256, false, false, QkvRopeEpi2>(x, w, B * N, 3 * E, E, 1, dummy, dummy, epi, st);
-  return launch_pair<128, false, false, QkvRopeEpi2>(x, w, B * N, 3 * E, E, 1, dummy, dummy, epi, st);
+  if (3 * E > 128) return launch_pair<256, false, false, QkvRopeEpi2>(x, w, B * N, 3 * E, E, 1, tplanes, tplanes, epi, st);
+  return launch_pair<128, false, false, QkvRopeEpi2>(x, w, B * N, 3 * E, E, 1, tplanes, tplanes, epi, st);
 }
 
 int patch_embed_gemm_tc2(const void* unfolded, const void* weight, const void* bias, const void* pos, void* tokens, int M,
