@@ -24,6 +24,15 @@
 //   * delta = rowsum(dO o O) and lse*log2(e) of the NEXT item are computed by a helper warp into shared memory
 //     while the current item runs (rows past N get lse = +inf -> P = 0).
 // Bias modes (relative table / polynomial) stay on variant 2 for now.
+//
+// Measured alternatives (ViT-B/16-224, B = 256; this kernel: 303 us, variant 2: 399 us):
+//   * one stream of all eight warps walking double-buffered 96-column groups with a TMA-store epilogue: 315 us - the
+//     S / dP waits disappear but twelve small groups per item cost as much in per-group overhead;
+//   * staging the outputs through 1 KB of shared memory per warp for coalesced stores: no gain (the 8-row rounds
+//     serialise); 32-byte TMA boxes need 4 KB per warp, which two resident items do not leave;
+//   * a second register buffer to keep the next chunk's tcgen05.ld in flight: slower (2 620 -> 3 400 cycles per 128
+//     columns).  The exponentials run at ~50-60 % of the MUFU roof (16 ex2 / clk / SM, scripts/ubench/mufu.cu) -
+//     P is evaluated twice per element (once per orientation), which is the price of keeping dS out of shared memory.
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"

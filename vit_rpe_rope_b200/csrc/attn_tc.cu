@@ -449,7 +449,7 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t ro
 }
 
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int swizzle128) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -462,8 +462,8 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VRR_REQUIRE(r == CUDA_SUCCESS, VRR_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
   return VRR_OK;
 }

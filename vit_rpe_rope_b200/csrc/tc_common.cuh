@@ -330,8 +330,9 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t ro
                  uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
 
 // 3-D bf16 map over [d2][d1][d0] (d0 innermost, contiguous), box = [1][box1][box0], box0 * 2 <= 128 bytes, 128-byte
-// swizzle.  Used for [B][N][E] activations: a box never crosses an image, rows past N are clipped by the hardware.
+// swizzle (or none: plain [box1][box0] staging).  Used for [B][N][E] activations and [planes][N][64] head planes: a
+// box never crosses an image / head, rows past N are clipped by the hardware (coordinates must not be negative).
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int swizzle128 = 1);
 
 }  // namespace vrr

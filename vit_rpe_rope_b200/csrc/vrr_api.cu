@@ -26,7 +26,7 @@ static std::atomic<int> g_dev_state[kMaxDevices];
 static std::atomic<int> g_dev_sms[kMaxDevices];
 std::atomic<uint64_t> g_family_launches[3];  // [VRR_IMPL_SIMT], [VRR_IMPL_TCGEN05] dispatch counters
 static std::atomic<int> g_attn_fwd_variant{3};  // 3: whole-sequence kernel for N <= 256 (attn_fwd_ws.cu), else attn_tc.cu; 2: attn_tc.cu always; 4: attn_fwd_tc3.cu for N > 256
-static std::atomic<int> g_attn_bwd_variant{3};  // 3: fused persistent kernel (attn_bwd_tc3.cu); 2: dQ + dK/dV kernels
+static std::atomic<int> g_attn_bwd_variant{3};  // 3: attn_bwd_ws.cu for N <= 208 without bias, else attn_bwd_tc2.cu; 2: attn_bwd_tc2.cu always
 
 int current_device() {
   int dev = 0;
@@ -374,7 +374,7 @@ int vrr_attn_bwd(const void* planes, const vrr_bias_desc* bias, const void* out,
   const int impl = g_impl.load();
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_bwd_tc2_supported(B, H, N, Dh, bias)) {
     VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
-    if (g_attn_bwd_variant.load() >= 3 && attn_bwd_ws_supported(B, H, N, Dh, bias))
+    if (g_attn_bwd_variant.load() >= 3 && attn_bwd_ws_supported(B, H, N, Dh, bias))  // short sequences, no bias
       return attn_bwd_ws(planes, out, d_out, lse, d_planes, B, H, N, Dh, scale, (cudaStream_t)stream);
     return attn_bwd_tc2(planes, bias, out, d_out, lse, d_planes, d_bias_param, delta, B, H, N, Dh, scale,
                         (cudaStream_t)stream);
