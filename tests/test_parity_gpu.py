@@ -632,3 +632,86 @@ def test_attention_properties_at_vitb_size(dtype, kind):
     got = oa[3].reshape(n, h, d)[:, 5].double().cpu().numpy()
     e = np.abs(got - o_row).max() / max(1.0, np.abs(o_row).max())
     assert e <= (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+
+
+# ------------------------------------------------------------------------------------- persistent kernels
+
+def _set_option(name, value):
+    _lib.check(_lib.load().vrr_set_option(name.encode(), int(value)), f"vrr_set_option({name})")
+
+
+@pytest.mark.parametrize("b,h,n", [(30, 12, 197), (40, 8, 65), (2, 3, 130), (171, 2, 197)])
+def test_persistent_attention_many_items_per_cta(b, h, n):
+    """The whole-sequence kernels (attn_fwd_ws.cu / attn_bwd_ws.cu) are persistent: with more (image, head) items
+    than SMs every CTA walks several items through its double-buffered shared memory, TMEM and barrier phases.
+    fwd + bwd of ALL items against float64 numpy (rotating-buffer bugs only show from the second item on), and
+    bit-for-bit run-to-run reproducibility of the forward (no atomics on this path)."""
+    d = 64
+    planes = _planes(b, h, n, d, torch.bfloat16, seed=21).to(DEV).requires_grad_(True)
+    g = torch.Generator().manual_seed(22)
+    d_out = (torch.randn(b, n, h * d, generator=g) * 0.5).to(torch.bfloat16)
+    scale = d ** -0.5
+    with tcgen05_must_run():
+        out = ops.fused_attention(planes, scale)
+        out.backward(d_out.to(DEV))
+    out2 = ops.fused_attention(planes.detach(), scale)
+    assert torch.equal(out, out2), "persistent forward is not reproducible run to run"
+    pl = planes.detach().double().cpu().numpy()
+    o_np, _, _, _ = A.attention_forward(pl[0], pl[1], pl[2], scale, None)
+    gr = A.attention_backward(d_out.double().numpy(), pl[0], pl[1], pl[2], scale, None, out=out.detach().double().cpu().numpy())
+    assert torch.isfinite(planes.grad).all()
+    assert err_rel(out.float(), o_np) <= BF16_TOL
+    # per item: a wrong item hides in a global max-norm when its neighbours are right
+    got = planes.grad.float().cpu().numpy().reshape(3, b * h, n, d)
+    want = np.stack([gr["dq"], gr["dk"], gr["dv"]]).reshape(3, b * h, n, d)
+    per_item = np.abs(got - want).max(axis=(2, 3)) / np.maximum(np.abs(want).max(axis=(2, 3)), 1e-6)
+    report(f"persistent attention b={b} h={h} n={n}: worst per-item grad err {per_item.max():.2e}")
+    assert per_item.max() <= 2 * BF16_TOL, (np.unravel_index(per_item.argmax(), per_item.shape), per_item.max())
+
+
+@pytest.mark.parametrize("n", [65, 197])
+def test_attention_kernel_variants_agree(n):
+    """A/B switches (vrr_set_option): the whole-sequence kernels against variant 2 (one CTA per 128-row tile; two
+    backward kernels) on the same inputs - two independent schedules of the same math."""
+    b, h, d = 6, 12, 64
+    planes = _planes(b, h, n, d, torch.bfloat16, seed=31).to(DEV)
+    g = torch.Generator().manual_seed(32)
+    d_out = (torch.randn(b, n, h * d, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    res = {}
+    try:
+        for variant in (3, 2):
+            _set_option("attn_fwd_variant", variant)
+            _set_option("attn_bwd_variant", variant)
+            pl = planes.clone().requires_grad_(True)
+            out = ops.fused_attention(pl, d ** -0.5)
+            out.backward(d_out)
+            res[variant] = (out.detach().float(), pl.grad.float())
+    finally:
+        _set_option("attn_fwd_variant", 3)
+        _set_option("attn_bwd_variant", 3)
+    assert err_rel(res[3][0], res[2][0].cpu().numpy()) <= 1e-2
+    assert err_rel(res[3][1], res[2][1].cpu().numpy()) <= BF16_TOL
+
+
+@pytest.mark.parametrize("m,n,k", [(394, 3072, 768), (130, 104, 72), (1000, 256, 520)])
+def test_gemm_epilogues_gelu_grad_and_mul(m, n, k):
+    """VRR_EPI_BIAS_GELU_GRAD (c = gelu(h), c2 = gelu'(h), h = bf16(a.b^T + bias)) and VRR_EPI_MUL (c = (a.b) * c2),
+    the pair that replaces the stand-alone GELU backward: against torch in fp32 on the bf16-rounded h."""
+    g = torch.Generator().manual_seed(5)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    with tcgen05_must_run():
+        act, gp = ops._gemm(a, w, False, True, torch.bfloat16, bias=bias, epilogue=_lib.EPI_BIAS_GELU_GRAD, out2=True)
+    h = (a.float() @ w.float().t() + bias.to(torch.bfloat16).float()).to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.gelu(h)
+    ref.sum().backward()
+    assert err_rel(act.float(), ref.detach().cpu().numpy()) <= 1e-2
+    assert err_rel(gp.float(), h.grad.cpu().numpy()) <= 1e-2
+    dy = (torch.randn(m, n, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    w2 = (torch.randn(n, k, generator=g) * n ** -0.5).to(torch.bfloat16).to(DEV)  # dX = dy . w2 -> [m, k]
+    mul = torch.randn(m, k, generator=g).to(torch.bfloat16).to(DEV)
+    with tcgen05_must_run():
+        dx = ops._gemm(dy, w2, False, False, torch.bfloat16, epilogue=_lib.EPI_MUL, aux=mul)
+    want = (dy.float() @ w2.float()) * mul.float()
+    assert err_rel(dx.float(), want.cpu().numpy()) <= 1e-2

@@ -2,7 +2,8 @@
 // whole-sequence variant.  Replaces models/vit.py:71-88 of the reference
 // (S = q k^T * scale (+ bias) -> softmax -> . v -> merge heads) without materialising S or P in HBM.
 //
-// Why a separate kernel.  clock64 timelines of the streaming kernels (attn_tc.cu, attn_fwd_tc3.cu) at 197 tokens
+// Why a separate kernel.  clock64 timelines of the streaming kernel (attn_tc.cu, and of a persistent two-group
+// variant of it that was measured and dropped: 147 us against 141 us) at 197 tokens
 // showed the time going to per-tile fixed costs, not to math: every 64-key tile costs the issuer ~4 mbarrier waits
 // (~90 cycles each even when already complete), ~16 small tcgen05.mma (N = 64: 32-48 cycles each at issue) and ~7
 // commits, and costs each softmax thread a wait / fence / arrive round trip - more than the tile's exponentials.

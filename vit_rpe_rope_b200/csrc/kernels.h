@@ -21,13 +21,6 @@ void attn_fwd_tc_set_debug(long long* buf);
 int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
                 int Dh, float scale, cudaStream_t st);
 
-// attn_fwd_tc3.cu (variant 3, default: persistent CTAs, two softmax warpgroups, cross-item prefetch)
-bool attn_fwd_tc3_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
-void attn_fwd_tc3_set_threshold_x100(int v);
-void attn_fwd_tc3_set_debug(long long* buf);
-int attn_fwd_tc3(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
-                 int Dh, float scale, cudaStream_t st);
-
 // attn_fwd_ws.cu (whole-sequence forward for N <= 256: persistent, one round trip per (image, head))
 bool attn_fwd_ws_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
 int attn_fwd_ws(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N, int Dh,

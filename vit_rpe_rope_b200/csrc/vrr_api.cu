@@ -25,7 +25,7 @@ constexpr int kMaxDevices = 64;
 static std::atomic<int> g_dev_state[kMaxDevices];
 static std::atomic<int> g_dev_sms[kMaxDevices];
 std::atomic<uint64_t> g_family_launches[3];  // [VRR_IMPL_SIMT], [VRR_IMPL_TCGEN05] dispatch counters
-static std::atomic<int> g_attn_fwd_variant{3};  // 3: whole-sequence kernel for N <= 256 (attn_fwd_ws.cu), else attn_tc.cu; 2: attn_tc.cu always; 4: attn_fwd_tc3.cu for N > 256
+static std::atomic<int> g_attn_fwd_variant{3};  // 3: whole-sequence kernel for N <= 256 (attn_fwd_ws.cu), else attn_tc.cu; 2: attn_tc.cu always
 static std::atomic<int> g_attn_bwd_variant{3};  // 3: attn_bwd_ws.cu for N <= 208 without bias, else attn_bwd_tc2.cu; 2: attn_bwd_tc2.cu always
 
 int current_device() {
@@ -138,7 +138,6 @@ uint64_t vrr_family_count(int family) {
 }
 int vrr_debug_timestamps(void* device_buf) {  /* 64 x int64 device buffer, or NULL to switch off */
   attn_fwd_tc_set_debug((long long*)device_buf);
-  attn_fwd_tc3_set_debug((long long*)device_buf);
   attn_bwd_ws_set_debug((long long*)device_buf);
   return VRR_OK;
 }
@@ -150,7 +149,6 @@ int vrr_set_option(const char* name, int value) {
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_rescale_threshold_x100")) {
     attn_fwd_tc_set_threshold_x100(value);
-    attn_fwd_tc3_set_threshold_x100(value);
     return VRR_OK;
   }
   set_error("vrr_set_option: unknown option '%s'", name);
@@ -337,8 +335,6 @@ int vrr_attn_fwd(const void* planes, const vrr_bias_desc* bias, void* out, float
     const int variant = g_attn_fwd_variant.load();
     if (variant >= 3 && attn_fwd_ws_supported(B, H, N, Dh, bias))  // short sequences: whole-sequence kernel
       return attn_fwd_ws(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
-    if (variant == 4 && attn_fwd_tc3_supported(B, H, N, Dh, bias))  // persistent streaming kernel (A/B only)
-      return attn_fwd_tc3(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
     return attn_fwd_tc(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
   }
   VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,
