@@ -24,6 +24,14 @@ struct StridedOperand {
   __device__ __forceinline__ float operator()(int r, int k) const {
     return Elem<T>::ld(p + (long long)r * s_row + (long long)k * s_k);
   }
+  // four consecutive elements along the contiguous dimension (k when s_k == 1, the row index when s_row == 1)
+  static constexpr bool kVec = true;
+  __device__ __forceinline__ bool vec_ok() const {
+    const long long other = s_k == 1 ? s_row : s_k;
+    return (s_k == 1 || s_row == 1) && (other & 3) == 0 && ((uintptr_t)p & 15) == 0;
+  }
+  __device__ __forceinline__ float4 ld4k(int r, int k) const { return ld4(p + (long long)r * s_row + k); }   // s_k == 1
+  __device__ __forceinline__ float4 ld4r(int r, int k) const { return ld4(p + (long long)k * s_k + r); }     // s_row == 1
 };
 
 // A[m][k] of unfold(images): m = b*Np + p (p = py*gw + px), k = c*P*P + i*P + j
@@ -31,6 +39,7 @@ struct StridedOperand {
 // images, i.e. the reference's autocast cast of the conv input fused into the load).
 template <typename TI, bool ROUND>
 struct Im2colOperand {
+  static constexpr bool kVec = false;
   const TI* img;
   int C, Hi, Wi, P, gw, Np;
   __device__ __forceinline__ float operator()(int m, int k) const {
@@ -44,6 +53,7 @@ struct Im2colOperand {
 // A'[e][m] = d_tokens[b][1+p][e] for the patch-embed weight gradient (m = b*Np + p)
 template <typename T>
 struct PatchGradOperand {
+  static constexpr bool kVec = false;
   const T* dtok;
   int Np, E;
   __device__ __forceinline__ float operator()(int e, int m) const {
@@ -54,6 +64,7 @@ struct PatchGradOperand {
 
 template <typename Inner>
 struct SwapArgs {  // view an operand (r,k) as (k,r)
+  static constexpr bool kVec = false;
   Inner in;
   __device__ __forceinline__ float operator()(int r, int k) const { return in(k, r); }
 };
@@ -192,8 +203,171 @@ __global__ void __launch_bounds__(GT) gemm_simt_kernel(AOp A, BOp Bop, Epi epi, 
   }
 }
 
+// ---- 128 x 128 tile variant ------------------------------------------------------------------------
+// The 64 x 64 kernel above is bound by shared-memory bandwidth (two LDS.128 per 16 FFMA) and by its scalar,
+// un-pipelined global loads: 25 TFLOP/s on the ViT-Tiny shapes (8320 x 768 x 192), a third of the FFMA roof and
+// slower than cuBLAS SGEMM - which made the fp32 configurations slower than the reference's own GPU path.  Here
+// each thread owns an 8 x 8 micro-tile as 2 x 2 blocks of 4 x 4 (four LDS.128 per 64 FFMA), the operand tiles are
+// double-buffered in shared memory with the next tile's global loads (128-bit when the operand is a plain
+// row-major matrix) in flight during the FFMAs, and the output tile is staged 64 rows at a time for the row-aware
+// epilogues.
+constexpr int TM = 128, TN = 128, TK = 16;
+constexpr int TLD = TM + 4;
+
+// ROWS = 128 or 64 rows of the operand tile; every thread moves ROWS / 16 elements per k-tile.
+//   KC  (operand contiguous along k): element e of half h -> (r = tid >> 2 + 64 h, k = 4 (tid & 3) + e)
+//   !KC (contiguous along the row index): ROWS = 128: (r = 4 (tid & 31) + e, k = tid >> 5 + 8 h); ROWS = 64: (r = 4 (tid & 15) + e, k = tid >> 4)
+template <typename Op, bool KC, int ROWS>
+__device__ __forceinline__ void load_tile(const Op& op, bool vec, int row0, int nrows, int k0, int k_end, int tid,
+                                          float (&reg)[ROWS / 16]) {
+  constexpr int H = ROWS / 64;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    int r, k;
+    if (KC) { r = (tid >> 2) + h * 64; k = (tid & 3) * 4; }
+    else if (ROWS == 128) { r = (tid & 31) * 4; k = (tid >> 5) + h * 8; }
+    else { r = (tid & 15) * 4; k = tid >> 4; }
+    bool done = false;
+    if constexpr (Op::kVec) {
+      if (vec && (KC ? (row0 + r < nrows && k0 + k + 3 < k_end) : (row0 + r + 3 < nrows && k0 + k < k_end))) {
+        const float4 v = KC ? op.ld4k(row0 + r, k0 + k) : op.ld4r(row0 + r, k0 + k);
+        reg[h * 4 + 0] = v.x; reg[h * 4 + 1] = v.y; reg[h * 4 + 2] = v.z; reg[h * 4 + 3] = v.w;
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rr = KC ? r : r + e, kk = KC ? k + e : k;
+        reg[h * 4 + e] = (row0 + rr < nrows && k0 + kk < k_end) ? op(row0 + rr, k0 + kk) : 0.f;
+      }
+    }
+  }
+}
+template <bool KC, int ROWS>
+__device__ __forceinline__ void store_tile(float* S, int tid, const float (&reg)[ROWS / 16]) {  // S: [TK][TLD], k-major
+  constexpr int H = ROWS / 64;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    if (KC) {
+      const int r = (tid >> 2) + h * 64, k = (tid & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) S[(k + e) * TLD + r] = reg[h * 4 + e];
+    } else {
+      const int r = ROWS == 128 ? (tid & 31) * 4 : (tid & 15) * 4, k = ROWS == 128 ? (tid >> 5) + h * 8 : tid >> 4;
+      *reinterpret_cast<float4*>(S + k * TLD + r) = make_float4(reg[h * 4], reg[h * 4 + 1], reg[h * 4 + 2], reg[h * 4 + 3]);
+    }
+  }
+}
+
+// NB = 1 or 2 blocks of 64 output columns (tile 128 x 64 or 128 x 128)
+template <typename AOp, typename BOp, typename Epi, bool A_KC, bool B_KC, int NB>
+__global__ void __launch_bounds__(GT, 2) gemm_simt128_kernel(AOp A, BOp Bop, Epi epi, int M, int N, int K, int k_per_split) {
+  constexpr int TNN = 64 * NB;
+  __shared__ __align__(16) float smem[4 * TK * TLD];  // A[2][TK][TLD] | B[2][TK][TLD]; reused as C staging [64][TNN + 1]
+  static_assert(4 * TK * TLD >= 64 * (TN + 1), "C staging does not fit");
+  float* As = smem;
+  float* Bs = smem + 2 * TK * TLD;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TNN;
+  const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  bool avec = false, bvec = false;
+  if constexpr (AOp::kVec) avec = A.vec_ok() && (A_KC ? A.s_k == 1 : A.s_row == 1);
+  if constexpr (BOp::kVec) bvec = Bop.vec_ok() && (B_KC ? Bop.s_k == 1 : Bop.s_row == 1);
+
+  float acc[2][NB][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][b][i][j] = 0.f;
+
+  float ra[8], rb[4 * NB];
+  load_tile<AOp, A_KC, 128>(A, avec, m0, M, k_begin, k_end, tid, ra);
+  load_tile<BOp, B_KC, TNN>(Bop, bvec, n0, N, k_begin, k_end, tid, rb);
+  store_tile<A_KC, 128>(As, tid, ra);
+  store_tile<B_KC, TNN>(Bs, tid, rb);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+    const bool more = k0 + TK < k_end;
+    if (more) {  // next tile's global loads in flight during the FFMAs
+      load_tile<AOp, A_KC, 128>(A, avec, m0, M, k0 + TK, k_end, tid, ra);
+      load_tile<BOp, B_KC, TNN>(Bop, bvec, n0, N, k0 + TK, k_end, tid, rb);
+    }
+    const float* Ac = As + buf * TK * TLD;
+    const float* Bc = Bs + buf * TK * TLD;
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float av[2][4], bv[NB][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const float4 v = *reinterpret_cast<const float4*>(Ac + k * TLD + a * 64 + ty * 4);
+        av[a][0] = v.x; av[a][1] = v.y; av[a][2] = v.z; av[a][3] = v.w;
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 v = *reinterpret_cast<const float4*>(Bc + k * TLD + b * 64 + tx * 4);
+        bv[b][0] = v.x; bv[b][1] = v.y; bv[b][2] = v.z; bv[b][3] = v.w;
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[a][b][i][j] = fmaf(av[a][i], bv[b][j], acc[a][b][i][j]);
+    }
+    if (more) {
+      store_tile<A_KC, 128>(As + (buf ^ 1) * TK * TLD, tid, ra);
+      store_tile<B_KC, TNN>(Bs + (buf ^ 1) * TK * TLD, tid, rb);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  // epilogue: 64 rows of the tile at a time through shared memory (row-aware epilogues see a whole output row)
+  float* Cs = smem;  // [64][TNN + 1]
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Cs[(ty * 4 + i) * (TNN + 1) + b * 64 + tx * 4 + j] = acc[a][b][i][j];
+    __syncthreads();
+    for (int e = tid; e < 64 * TNN; e += GT) {
+      const int r = e / TNN, c = e - r * TNN;
+      const int m = m0 + a * 64 + r;
+      if (m < M && n0 + c < N) epi(m, n0 + c, Cs[r * (TNN + 1) + c], Cs + r * (TNN + 1), n0);
+    }
+    __syncthreads();
+  }
+}
+
+std::atomic<int> g_simt_tile{128};  // 128: the 128 x 128 kernel when the problem has at least one full tile; 64: always 64 x 64
+
 template <typename AOp, typename BOp, typename Epi, bool A_KC, bool B_KC>
 static int launch_gemm(AOp A, BOp Bop, Epi epi, int M, int N, int K, int splits, cudaStream_t st) {
+  if (g_simt_tile.load() == 128 && M >= TM && N >= 64) {
+    // 128 x 128 tiles unless the last one would be at most half full (192, 576 columns, ...): then 128 x 64
+    const int rem = N % TN;
+    const bool narrow = N < TN || (rem > 0 && rem <= 64);
+    int kps = ceil_div(ceil_div(K, splits), TK) * TK;
+    if (narrow) {
+      dim3 grid(ceil_div(N, 64), ceil_div(M, TM), splits);
+      gemm_simt128_kernel<AOp, BOp, Epi, A_KC, B_KC, 1><<<grid, GT, 0, st>>>(A, Bop, epi, M, N, K, kps);
+    } else {
+      dim3 grid(ceil_div(N, TN), ceil_div(M, TM), splits);
+      gemm_simt128_kernel<AOp, BOp, Epi, A_KC, B_KC, 2><<<grid, GT, 0, st>>>(A, Bop, epi, M, N, K, kps);
+    }
+    VRR_LAUNCHED();
+    return VRR_OK;
+  }
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
   int kps = ceil_div(ceil_div(K, splits), BK) * BK;
   gemm_simt_kernel<AOp, BOp, Epi, A_KC, B_KC><<<grid, GT, 0, st>>>(A, Bop, epi, M, N, K, kps);
@@ -227,7 +401,9 @@ static int gemm_t(const void* a, const void* b, void* c, int M, int N, int K, in
   StridedOperand<T> A = ta ? StridedOperand<T>{(const T*)a, 1, M} : StridedOperand<T>{(const T*)a, K, 1};
   // Bop(n,k) = op(B)[k][n]: !tb -> b[k*N + n] (n contiguous) ; tb -> b[n*K + k] (k contiguous)
   StridedOperand<T> Bo = tb ? StridedOperand<T>{(const T*)b, K, 1} : StridedOperand<T>{(const T*)b, 1, N};
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const bool big = g_simt_tile.load() == 128 && M >= TM && N >= 64;
+  const bool narrow = N < TN || (N % TN > 0 && N % TN <= 64);
+  const int tiles = big ? ceil_div(M, TM) * ceil_div(N, narrow ? 64 : TN) : ceil_div(M, BM) * ceil_div(N, BN);
   int splits = 1;
   if (sizeof(TC) == 4) {
     const int want = 2 * sm_count();
@@ -267,6 +443,8 @@ int gemm_simt_bias(const void* a, const void* b, void* c, void* c2, const float*
   if (dtype == VRR_F32) return gemm_bias_t<float>(a, b, c, c2, bias, M, N, K, ta, tb, gelu, st);
   return gemm_bias_t<__nv_bfloat16>(a, b, c, c2, bias, M, N, K, ta, tb, gelu, st);
 }
+
+void gemm_simt_set_tile(int v) { g_simt_tile.store(v == 64 ? 64 : 128); }
 
 int gemm_simt(const void* a, const void* b, void* c, int M, int N, int K, int ta, int tb, int dtype,
               int c_dtype, cudaStream_t st) {
