@@ -53,7 +53,9 @@ def _worker(rank, world, port, out, style="dp_zero_grad"):
         opt = torch.optim.SGD(net.parameters(), lr=0.0)  # lr 0: weights stay put, only the zeroing style matters
         for step in range(3):  # later steps check zeroing / re-arming of the buckets
             if style == "dp_zero_grad":
-                dp.zero_grad()
+                dp.zero_grad()           # default: gradients dropped, autograd's tensors adopted, one gather per bucket
+            elif style == "dp_zero_in_place":
+                dp.zero_grad(set_to_none=False)  # gradients stay views of the zeroed buckets
             else:  # the reference loop (train.py:111): set_to_none=True unbinds every p.grad from its bucket
                 opt.zero_grad()
             if style == "accumulate":  # two half-shards: the first backward only accumulates locally
@@ -77,7 +79,7 @@ def _worker(rank, world, port, out, style="dp_zero_grad"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("style", ["dp_zero_grad", "optimizer_zero_grad", "accumulate"])
+@pytest.mark.parametrize("style", ["dp_zero_grad", "dp_zero_in_place", "optimizer_zero_grad", "accumulate"])
 def test_bucketed_dp_matches_single_process(style):
     world = 2
     port = _free_port()
