@@ -23,7 +23,10 @@
 //     behind the accumulating MMAs that read the columns they overwrite;
 //   * delta = rowsum(dO o O) and lse*log2(e) of the NEXT item are computed by a helper warp into shared memory
 //     while the current item runs (rows past N get lse = +inf -> P = 0).
-// Bias modes (relative table / polynomial) stay on variant 2 for now.
+// Bias modes (relative table / polynomial) stay on variant 2: a version of this kernel with the bias in the exponent
+// of both orientations and the gradients taken in the dQ tiles (systolic diagonal sums into a shared histogram;
+// per-thread power sums) was built and was correct, but its per-element extras made it slower than variant 2
+// (relative table 1 104 us against 856 us, polynomial 716 us against 627 us at ViT-B) - not kept.
 //
 // Measured alternatives (ViT-B/16-224, B = 256; this kernel: 303 us, variant 2: 399 us):
 //   * one stream of all eight warps walking double-buffered 96-column groups with a TMA-store epilogue: 315 us - the
