@@ -39,6 +39,7 @@ int attn_bwd_ws(const void* planes, const void* out, const void* d_out, const fl
                 int N, int Dh, float scale, cudaStream_t st);
 
 // gemm_simt.cu
+void layernorm_set_option(int which, int value);  // 0: ln_reg, 1: ln_bwd_minb
 void gemm_simt_set_tile(int v);  // 128 (default): 128 x 128 double-buffered kernel for problems with a full tile; 64: 64 x 64 always
 int qkv_rope_fwd_simt(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes,
                       int B, int N, int E, int H, int rope_mode, int dtype, cudaStream_t st);

@@ -20,6 +20,8 @@ namespace vrr {
 namespace {
 
 constexpr int kLnWarps = 8;
+static int g_ln_bwd_minb = 3;  // register-resident add_ln_bwd at E >= 768: 3 = 12 warps x 1 CTA/SM (E = 768), 1 = 8 x 1, 2 = 8 x 2 (spills)
+static int g_ln_reg = 1;       // 0: generic multi-pass kernels only (option "ln_reg")
 
 // resident CTAs per SM the backward's shared-memory partials allow (2 x warps x E floats per CTA)
 static inline int ln_bwd_ctas_per_sm(int E) {
@@ -361,10 +363,161 @@ add_ln_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ d_xnew, c
   }
 }
 
+// ---- register-resident rows (E = 128 NV, NV <= 8: ViT-B 768, ViT-L 1024) ---------------------------------------
+// The generic kernels above re-read the row from L1 for every pass (three passes forward, two backward) and keep
+// the gamma / beta gradient partials in shared memory with a read-modify-write per element and row: 99 / 138 us at
+// ViT-B where the HBM floor is 71 / 95 us.  Here a lane keeps its NV float4 of the row in registers across the
+// passes and its slice of the dgamma / dbeta partial sums in registers across ROWS (a lane owns the same columns
+// for every row), touching shared memory once per CTA for the cross-warp reduction.  Same operation order per
+// element as the generic kernels, so the results are bit-identical to them.
+template <typename TB, typename TY, int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_ln_fwd_reg_kernel(const float* __restrict__ x, const TB* __restrict__ branch, float* __restrict__ x_new,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, TY* __restrict__ y,
+                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, float eps) {
+  constexpr int E = NV * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_e = 1.f / (float)E;
+  float4 g[NV], bt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = ld4(gamma + lane * 4 + i * 128);
+    bt[i] = ld4(beta + lane * 4 + i * 128);
+  }
+  for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+    const float* xr = x + (size_t)row * E + lane * 4;
+    const TB* br = branch + (size_t)row * E + lane * 4;
+    float* nr = x_new + (size_t)row * E + lane * 4;
+    TY* yr = y + (size_t)row * E + lane * 4;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = ld4(xr + i * 128), b = ld4(br + i * 128);
+      v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      st4(nr + i * 128, v[i]);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * inv_e;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_e + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x;
+      o.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
+      o.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z;
+      o.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
+      st4(yr + i * 128, o);
+    }
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+template <typename TB, typename TY, int NV, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+add_ln_bwd_reg_kernel(const TY* __restrict__ dy, const float* __restrict__ d_xnew, const float* __restrict__ x_new,
+                      const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                      float* __restrict__ dx, TB* __restrict__ d_branch, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, int M) {
+  constexpr int E = NV * 128;
+  extern __shared__ __align__(16) float ln_smem[];  // [2][WARPS][E], used once at the end
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_e = 1.f / (float)E;
+  float4 pg[NV], pb[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) pg[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    const TY* gr = dy + (size_t)row * E + lane * 4;
+    const float* xr = x_new + (size_t)row * E + lane * 4;
+    const float* rr = d_xnew ? d_xnew + (size_t)row * E + lane * 4 : nullptr;
+    float* dr = dx + (size_t)row * E + lane * 4;
+    TB* br = d_branch + (size_t)row * E + lane * 4;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 g[NV], xh[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      g[i] = ld4(gr + i * 128);
+      xh[i] = ld4(xr + i * 128);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(gamma + lane * 4 + i * 128));
+      xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd, (xh[i].w - mean) * rstd);
+      const float gw[4] = {g[i].x * w.x, g[i].y * w.y, g[i].z * w.z, g[i].w * w.w};
+      const float xv[4] = {xh[i].x, xh[i].y, xh[i].z, xh[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s1 += gw[e];
+        s2 = fmaf(gw[e], xv[e], s2);
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_e, c2 = warp_sum(s2) * inv_e;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(gamma + lane * 4 + i * 128));
+      const float4 r = rr ? ld4(rr + i * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = r.x + rstd * (g[i].x * w.x - c1 - xh[i].x * c2);
+      o.y = r.y + rstd * (g[i].y * w.y - c1 - xh[i].y * c2);
+      o.z = r.z + rstd * (g[i].z * w.z - c1 - xh[i].z * c2);
+      o.w = r.w + rstd * (g[i].w * w.w - c1 - xh[i].w * c2);
+      st4(dr + i * 128, o);
+      st4(br + i * 128, o);
+      pg[i].x = fmaf(g[i].x, xh[i].x, pg[i].x);
+      pg[i].y = fmaf(g[i].y, xh[i].y, pg[i].y);
+      pg[i].z = fmaf(g[i].z, xh[i].z, pg[i].z);
+      pg[i].w = fmaf(g[i].w, xh[i].w, pg[i].w);
+      pb[i].x += g[i].x;
+      pb[i].y += g[i].y;
+      pb[i].z += g[i].z;
+      pb[i].w += g[i].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    *reinterpret_cast<float4*>(ln_smem + (size_t)warp * E + lane * 4 + i * 128) = pg[i];
+    *reinterpret_cast<float4*>(ln_smem + (size_t)(WARPS + warp) * E + lane * 4 + i * 128) = pb[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += WARPS * 32) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      sg += ln_smem[(size_t)w * E + c];
+      sb += ln_smem[(size_t)(WARPS + w) * E + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
 template <typename TB, typename TY>
 int add_ln_fwd_t(const float* x, const void* branch, float* x_new, const float* gamma, const float* beta, void* y,
                  float* mean, float* rstd, int M, int E, float eps, cudaStream_t st) {
   const int grid = min(ceil_div(M, kLnWarps), 8 * sm_count());
+#define VRR_LN_REG(NV)                                                                                                \
+  if (g_ln_reg && E == NV * 128) { \
+    const int g2 = min(ceil_div(M, kLnWarps), 4 * sm_count());                                                        \
+    add_ln_fwd_reg_kernel<TB, TY, NV><<<g2, kLnWarps * 32, 0, st>>>(x, (const TB*)branch, x_new, gamma, beta, (TY*)y, \
+                                                                    mean, rstd, M, eps);                              \
+    VRR_LAUNCHED();                                                                                                   \
+    return VRR_OK;                                                                                                    \
+  }
+  VRR_LN_REG(6) VRR_LN_REG(8) VRR_LN_REG(4) VRR_LN_REG(2)
+#undef VRR_LN_REG
   if (E % 128 == 0)
     add_ln_fwd_kernel<TB, TY, 4><<<grid, kLnWarps * 32, 0, st>>>(x, (const TB*)branch, x_new, gamma, beta, (TY*)y, mean, rstd, M, E, eps);
   else
@@ -392,6 +545,26 @@ int add_ln_bwd_t(const void* dy, const float* d_xnew, const float* x_new, const 
                  cudaStream_t st) {
   VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
   VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+#define VRR_LN_BWD_GO(NV, W, B)                                                                                          \
+  auto kern = add_ln_bwd_reg_kernel<TB, TY, NV, W, B>;                                                                 \
+  VRR_SMEM_ATTR_ONCE(kern, 160 * 1024);                                                                                \
+  const int grid = min(ceil_div(M, W), B * sm_count());                                                                \
+  kern<<<grid, W * 32, (size_t)2 * W * E * sizeof(float), st>>>((const TY*)dy, d_xnew, x_new, gamma, mean, rstd, dx,   \
+                                                                (TB*)d_branch, dgamma, dbeta, M);
+#define VRR_LN_REG(NV)                                                                                                  \
+  if (g_ln_reg && E == NV * 128) { \
+    if (NV <= 4 || g_ln_bwd_minb == 2) {                                                                                \
+      VRR_LN_BWD_GO(NV, 8, 2)                                                                                              \
+    } else if (g_ln_bwd_minb == 1 || NV > 6) {                                                                               \
+      VRR_LN_BWD_GO(NV, 8, 1)                                                                                              \
+    } else {                                                                                                            \
+      VRR_LN_BWD_GO(NV, 12, 1)                                                                                             \
+    }                                                                                                                   \
+    VRR_LAUNCHED();                                                                                                     \
+    return VRR_OK;                                                                                                      \
+  }
+  VRR_LN_REG(6) VRR_LN_REG(8) VRR_LN_REG(4) VRR_LN_REG(2)
+#undef VRR_LN_REG
   if (E % 128 == 0)
     return add_ln_bwd_launch<TB, TY, 4>(dy, d_xnew, x_new, gamma, mean, rstd, dx, d_branch, dgamma, dbeta, M, E, st);
   return add_ln_bwd_launch<TB, TY, 1>(dy, d_xnew, x_new, gamma, mean, rstd, dx, d_branch, dgamma, dbeta, M, E, st);
@@ -450,6 +623,11 @@ int add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new, con
 #undef ARGS
   set_error("add_layernorm_bwd: unsupported dtype combination (branch %d, y %d)", branch_dtype, y_dtype);
   return VRR_ERR_UNSUPPORTED;
+}
+
+void layernorm_set_option(int which, int value) {
+  if (which == 0) g_ln_reg = value != 0;
+  if (which == 1) g_ln_bwd_minb = value;
 }
 
 }  // namespace vrr

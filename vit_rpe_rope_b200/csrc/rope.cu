@@ -13,9 +13,12 @@ template <typename T, int VEC>
 struct VecIO;
 template <>
 struct VecIO<float, 4> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
-    const float4 x = *reinterpret_cast<const float4*>(p);
+  using Raw = float4;
+  static __device__ __forceinline__ void cvt(const float4& x, float (&v)[4]) {
     v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    cvt(*reinterpret_cast<const float4*>(p), v);
   }
   static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -23,14 +26,17 @@ struct VecIO<float, 4> {
 };
 template <>
 struct VecIO<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 x = *reinterpret_cast<const uint4*>(p);
+  using Raw = uint4;
+  static __device__ __forceinline__ void cvt(const uint4& x, float (&v)[8]) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
       v[2 * e] = f.x; v[2 * e + 1] = f.y;
     }
+  }
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    cvt(*reinterpret_cast<const uint4*>(p), v);
   }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 x;
@@ -64,14 +70,30 @@ __global__ void qkv_rope_bwd_kernel(const T* __restrict__ d_planes, const T* __r
     for (int e = 0; e < VEC; ++e) { c[e] = cos_tab[tab + e]; s[e] = sin_tab[tab + e]; }
   }
   const bool want_cs = rot && d_cos != nullptr;
+  // All ten 16-byte loads of one image are issued before the first use (raw, converted when consumed): with the
+  // loads interleaved with the stores a thread had 32 bytes in flight and the kernel ran at a third of the HBM rate.
+  using Raw = typename VecIO<T, VEC>::Raw;
   for (int b = b0; b < b1; ++b) {
     const size_t src = (((size_t)b * H + h) * N + t) * Dh + dd;
     T* dst = d_qkv + ((size_t)b * N + t) * (3 * E) + h * Dh + dd;
+    Raw rg[3][2], rx[2][2];
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      rg[which][0] = *reinterpret_cast<const Raw*>(d_planes + which * plane + src);
+      rg[which][1] = *reinterpret_cast<const Raw*>(d_planes + which * plane + src + hd);
+    }
+    if (want_cs) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        rx[which][0] = *reinterpret_cast<const Raw*>(planes + which * plane + src);
+        rx[which][1] = *reinterpret_cast<const Raw*>(planes + which * plane + src + hd);
+      }
+    }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       float g1[VEC], g2[VEC], o1[VEC], o2[VEC];
-      VecIO<T, VEC>::ld(d_planes + which * plane + src, g1);
-      VecIO<T, VEC>::ld(d_planes + which * plane + src + hd, g2);
+      VecIO<T, VEC>::cvt(rg[which][0], g1);
+      VecIO<T, VEC>::cvt(rg[which][1], g2);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         o1[e] = g1[e] * c[e] + g2[e] * s[e];
@@ -81,8 +103,8 @@ __global__ void qkv_rope_bwd_kernel(const T* __restrict__ d_planes, const T* __r
       VecIO<T, VEC>::st(dst + which * E + hd, o2);
       if (want_cs) {
         float r1[VEC], r2[VEC];
-        VecIO<T, VEC>::ld(planes + which * plane + src, r1);
-        VecIO<T, VEC>::ld(planes + which * plane + src + hd, r2);
+        VecIO<T, VEC>::cvt(rx[which][0], r1);
+        VecIO<T, VEC>::cvt(rx[which][1], r2);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const float x1 = r1[e] * c[e] + r2[e] * s[e], x2 = r2[e] * c[e] - r1[e] * s[e];  // un-rotated
@@ -91,11 +113,8 @@ __global__ void qkv_rope_bwd_kernel(const T* __restrict__ d_planes, const T* __r
         }
       }
     }
-    float v1[VEC], v2[VEC];
-    VecIO<T, VEC>::ld(d_planes + 2 * plane + src, v1);
-    VecIO<T, VEC>::ld(d_planes + 2 * plane + src + hd, v2);
-    VecIO<T, VEC>::st(dst + 2 * E, v1);
-    VecIO<T, VEC>::st(dst + 2 * E + hd, v2);
+    *reinterpret_cast<Raw*>(dst + 2 * E) = rg[2][0];
+    *reinterpret_cast<Raw*>(dst + 2 * E + hd) = rg[2][1];
   }
   if (want_cs) {
 #pragma unroll

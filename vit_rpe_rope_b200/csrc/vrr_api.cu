@@ -145,6 +145,8 @@ int vrr_set_option(const char* name, int value) {
   if (!name) return VRR_ERR_INVALID_ARG;
   if (!strcmp(name, "gemm_variant")) { gemm_tc_set_variant(value); return VRR_OK; }
   if (!strcmp(name, "simt_gemm_tile")) { gemm_simt_set_tile(value); return VRR_OK; }
+  if (!strcmp(name, "ln_reg")) { layernorm_set_option(0, value); return VRR_OK; }
+  if (!strcmp(name, "ln_bwd_minb")) { layernorm_set_option(1, value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_variant")) { g_attn_fwd_variant.store(value); return VRR_OK; }
   if (!strcmp(name, "attn_bwd_variant")) { g_attn_bwd_variant.store(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
