@@ -12,6 +12,69 @@ namespace {
 constexpr int kCsThreads = 256;   // 32 column-quads x 8 row lanes
 constexpr int kCsRows = 256;      // rows per CTA
 
+// 16-byte loads, eight of them in flight per thread: thread = VEC consecutive columns (8 bf16 / 4 fp32) x rows
+// rl, rl + 16, ...; CTA = 16 column groups x 16 row lanes over kCsRows rows; grid (ceil(C / (16 VEC)), ceil(M / 256)).
+// (The first version read 8 bytes per thread and row with a rolled loop: 38 us average over the step's bias
+// gradients where the HBM floor is 24 us.)
+template <typename T>
+struct CsVec;
+template <>
+struct CsVec<float> {
+  static constexpr int kVec = 4;
+  using Raw = float4;
+  static __device__ __forceinline__ void add(float (&acc)[4], const float4& v) {
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  }
+};
+template <>
+struct CsVec<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  using Raw = uint4;
+  static __device__ __forceinline__ void add(float (&acc)[8], const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+      acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int C) {
+  constexpr int VEC = CsVec<T>::kVec;
+  using Raw = typename CsVec<T>::Raw;
+  __shared__ float part[16][16 * VEC + 1];
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c = (blockIdx.x * 16 + cg) * VEC;
+  const int r0 = blockIdx.y * kCsRows + rl, r1 = min(M, blockIdx.y * kCsRows + kCsRows);
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  if (c < C) {
+    const T* p = x + (size_t)r0 * C + c;
+    int r = r0;
+    for (; r + 7 * 16 < r1; r += 8 * 16, p += (size_t)8 * 16 * C) {
+      Raw v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const Raw*>(p + (size_t)k * 16 * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) CsVec<T>::add(acc, v[k]);
+    }
+    for (; r < r1; r += 16, p += (size_t)16 * C) CsVec<T>::add(acc, *reinterpret_cast<const Raw*>(p));
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) part[rl][cg * VEC + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 16 * VEC) {
+    const int col = blockIdx.x * 16 * VEC + threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += part[k][threadIdx.x];
+    if (col < C) atomicAdd(out + col, s);
+  }
+}
+
 // grid (ceil(C / 128), ceil(M / kCsRows)); thread = 4 consecutive columns x strided rows
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int C) {
@@ -132,6 +195,14 @@ int mul_inplace(void* c, const void* m, size_t n, int dtype, cudaStream_t st) {
 int colsum(const void* x, float* out, int M, int C, int dtype, cudaStream_t st) {
   VRR_REQUIRE(C % 4 == 0, VRR_ERR_UNSUPPORTED, "colsum: C = %d must be a multiple of 4", C);
   VRR_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
+  const int vec = dtype == VRR_F32 ? 4 : 8;
+  if (C % vec == 0 && ((uintptr_t)x & 15) == 0) {
+    dim3 grid(ceil_div(C, 16 * vec), ceil_div(M, kCsRows));
+    if (dtype == VRR_F32) colsum_vec_kernel<float><<<grid, kCsThreads, 0, st>>>((const float*)x, out, M, C);
+    else colsum_vec_kernel<__nv_bfloat16><<<grid, kCsThreads, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
+    VRR_LAUNCHED();
+    return VRR_OK;
+  }
   dim3 grid(ceil_div(C, 128), ceil_div(M, kCsRows));
   if (dtype == VRR_F32) colsum_kernel<float><<<grid, kCsThreads, 0, st>>>((const float*)x, out, M, C);
   else colsum_kernel<__nv_bfloat16><<<grid, kCsThreads, 0, st>>>((const __nv_bfloat16*)x, out, M, C);

@@ -178,8 +178,10 @@ class RoPEMixed(nn.Module):
         t_x, t_y = self.init_t_xy(side, side, device)
         t_x, t_y = t_x.to(self.freqs.device), t_y.to(self.freqs.device)
         with torch.autocast("cuda", enabled=False):  # the table stays fp32 under CUDA autocast (:334)
-            phase_x = t_x.unsqueeze(-1) @ self.freqs[0].unsqueeze(-2)  # [H, N, D/2]
-            phase_y = t_y.unsqueeze(-1) @ self.freqs[1].unsqueeze(-2)
+            # the reference's [N,1] @ [H,1,D/2] outer products (K = 1: one exact product per element), written as
+            # broadcast multiplies so that no library GEMM is launched for them
+            phase_x = t_x.view(1, -1, 1) * self.freqs[0].unsqueeze(-2)  # [H, N, D/2]
+            phase_y = t_y.view(1, -1, 1) * self.freqs[1].unsqueeze(-2)
             phase_x = phase_x.view(seq_len, self.num_heads, -1).permute(1, 0, 2)
             phase_y = phase_y.view(seq_len, self.num_heads, -1).permute(1, 0, 2)
             phase = phase_x + phase_y
