@@ -75,7 +75,8 @@ typedef enum {
   VRR_EPI_BIAS = 1,            /* c = acc + bias                                                              */
   VRR_EPI_BIAS_GELU = 2,       /* c = h = acc + bias, c2 = gelu(h)            (exact erf GELU, timm Mlp)        */
   VRR_EPI_BIAS_GELU_GRAD = 3,  /* c = gelu(h), c2 = d gelu / dh (h)           (what the Mlp backward needs)     */
-  VRR_EPI_MUL = 4              /* c = acc * c2[m][n]; c2 is an INPUT [M][N]   (d_act * gelu'(h) in fc2's dX)    */
+  VRR_EPI_MUL = 4,             /* c = acc * c2[m][n]; c2 is an INPUT [M][N]   (d_act * gelu'(h) in fc2's dX)    */
+  VRR_EPI_BIAS_GELU_ACT = 5    /* c = gelu(acc + bias), c2 unused             (the Mlp under torch.no_grad)     */
 } vrr_epilogue;
 
 typedef struct {

@@ -708,6 +708,12 @@ def test_gemm_epilogues_gelu_grad_and_mul(m, n, k):
     ref.sum().backward()
     assert err_rel(act.float(), ref.detach().cpu().numpy()) <= 1e-2
     assert err_rel(gp.float(), h.grad.cpu().numpy()) <= 1e-2
+    with tcgen05_must_run():  # the inference epilogue: the same activation, alone
+        act_only = ops._gemm(a, w, False, True, torch.bfloat16, bias=bias, epilogue=_lib.EPI_BIAS_GELU_ACT)
+    assert torch.equal(act_only, act)
+    a32, w32 = a.float(), w.float()  # SIMT family (fp32): c = gelu(h) alone against torch
+    act32 = ops._gemm(a32, w32, False, True, torch.float32, bias=bias, epilogue=_lib.EPI_BIAS_GELU_ACT)
+    assert err_rel(act32, F.gelu(a32 @ w32.t() + bias).cpu().numpy()) <= 1e-5
     dy = (torch.randn(m, n, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
     w2 = (torch.randn(n, k, generator=g) * n ** -0.5).to(torch.bfloat16).to(DEV)  # dX = dy . w2 -> [m, k]
     mul = torch.randn(m, k, generator=g).to(torch.bfloat16).to(DEV)

@@ -17,7 +17,7 @@ VRR_F32, VRR_BF16 = 0, 1
 ROPE_NONE, ROPE_AXIAL, ROPE_MIXED = 0, 1, 2
 BIAS_NONE, BIAS_TABLE, BIAS_POLY = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_GRAD, EPI_MUL = 0, 1, 2, 3, 4
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_GRAD, EPI_MUL, EPI_BIAS_GELU_ACT = 0, 1, 2, 3, 4, 5
 
 STATUS_NAMES = {0: "VRR_OK", -1: "VRR_ERR_INVALID_ARG", -2: "VRR_ERR_UNSUPPORTED",
                 -3: "VRR_ERR_NO_DEVICE", -4: "VRR_ERR_CUDA", -5: "VRR_ERR_WORKSPACE"}

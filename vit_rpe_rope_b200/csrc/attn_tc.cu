@@ -385,6 +385,291 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p)
   if (warp == 4) tmem_dealloc(tmem_base, kV2TmemCols);
 }
 
+// =====================================================================================================
+// Variant 4 (default for N > 256 without bias): the same tile loop with HALF the on-chip footprint per CTA and four
+// CTAs per SM.  Variant 2 at 1025 tokens runs at ~45 % of the exponential (MUFU) roof: with two CTAs per SM a
+// scheduler holds two softmax warps, and each of them spends about half of a tile waiting (S barrier, tcgen05.ld,
+// tcgen05.st, P barrier).  Here a CTA keeps ONE S buffer (P written in place, the next S issued right behind the PV
+// MMA that reads it - the tensor pipe executes in issue order), a 2-stage K / V ring and 128 TMEM columns (S/P
+// [0,64), O [64,128)), so four CTAs = four independent streams share an SM: a stream's barrier and tensor-pipe
+// latencies are covered by the other three.  Registers are capped at ~100 by the residency, so a softmax thread
+// walks its row twice (max pass, exp pass) in 16-column chunks re-read from TMEM, the next chunk's tcgen05.ld in
+// flight behind the current one's arithmetic; scale-and-subtract and the row sum run on the packed fp32x2 pipe.
+constexpr int kV4Stages = 2, kV4Threads = 160;
+constexpr uint32_t kV4TmemCols = 128, kV4ColO = 64;
+constexpr int kV4NumBars = 4 * kV4Stages + 4;
+
+__device__ __forceinline__ float v4_max16(const uint32_t (&r)[16], float mx) {
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+  return mx;
+}
+template <bool FULL>
+__device__ __forceinline__ float v4_max16m(const uint32_t (&r)[16], float mx, int first, int nvalid) {
+  if constexpr (FULL) {
+    return v4_max16(r, mx);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (first + e < nvalid) mx = fmaxf(mx, __uint_as_float(r[e]));
+    return mx;
+  }
+}
+// P = 2^(s * scale - m) for 16 scores -> 8 packed bf16x2; the row sum accumulates in l2
+template <bool FULL>
+__device__ __forceinline__ void v4_exp16(const uint32_t (&r)[16], uint32_t (&pk)[8], float2 sc2, float2 nm2, float2& l2,
+                                         int first, int nvalid) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2);
+    float2 pv = make_float2(ex2(x.x), ex2(x.y));
+    if (!FULL) {
+      if (first + 2 * e >= nvalid) pv.x = 0.f;
+      if (first + 2 * e + 1 >= nvalid) pv.y = 0.f;
+    }
+    l2 = __fadd2_rn(l2, pv);
+    pk[e] = pack_bf16(pv.x, pv.y);
+  }
+}
+
+// one key tile of one query row: lazy reference-max update, then P over the first 32 of the 64 columns S occupied
+template <bool FULL>
+__device__ __forceinline__ void v4_tile(uint32_t trow, int nvalid, int t, float scale_log2, float thr, float& m_ref,
+                                        float& l_run) {
+  uint32_t a[16], b[16];
+  // ---- pass 1: tile max ----
+  float tmax = -INFINITY;
+  tmem_ld16(trow, a);
+  tmem_wait_ld();
+  tmem_ld16(trow + 16, b);
+  tmax = v4_max16m<FULL>(a, tmax, 0, nvalid);
+  tmem_wait_ld();
+  tmem_ld16(trow + 32, a);
+  tmax = v4_max16m<FULL>(b, tmax, 16, nvalid);
+  tmem_wait_ld();
+  tmem_ld16(trow + 48, b);
+  tmax = v4_max16m<FULL>(a, tmax, 32, nvalid);
+  tmem_wait_ld();
+  tmem_ld16(trow, a);  // first chunk of pass 2
+  tmax = v4_max16m<FULL>(b, tmax, 48, nvalid) * scale_log2;
+  const bool jump = tmax > m_ref + thr;
+  if (__any_sync(0xffffffffu, jump)) {
+    const float m_new = fmaxf(m_ref, tmax);
+    if (t > 0) {
+      // PV(t-1) has retired: bar_s(t) was committed behind it
+      const float f = ex2(m_ref - m_new);  // 1 for rows whose reference did not move
+      l_run *= f;
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        tmem_ld16(trow + kV4ColO + q * 16, b);
+        tmem_wait_ld();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) b[d] = __float_as_uint(__uint_as_float(b[d]) * f);
+        tmem_st16(trow + kV4ColO + q * 16, b);
+      }
+    }
+    m_ref = m_new;
+  }
+  // ---- pass 2 ----
+  const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+  float2 l2 = make_float2(0.f, 0.f);
+  uint32_t pk[8];
+  tmem_wait_ld();
+  tmem_ld16(trow + 16, b);
+  v4_exp16<FULL>(a, pk, sc2, nm2, l2, 0, nvalid);
+  tmem_st8(trow, pk);  // columns [0,8): scores already consumed
+  tmem_wait_ld();
+  tmem_ld16(trow + 32, a);
+  v4_exp16<FULL>(b, pk, sc2, nm2, l2, 16, nvalid);
+  tmem_st8(trow + 8, pk);
+  tmem_wait_ld();
+  tmem_ld16(trow + 48, b);
+  v4_exp16<FULL>(a, pk, sc2, nm2, l2, 32, nvalid);
+  tmem_st8(trow + 16, pk);
+  tmem_wait_ld();
+  v4_exp16<FULL>(b, pk, sc2, nm2, l2, 48, nvalid);
+  tmem_st8(trow + 24, pk);
+  l_run += l2.x + l2.y;
+  tmem_wait_st();
+}
+
+__global__ void __launch_bounds__(kV4Threads, 4)
+attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
+  constexpr int kKT = kV2KT, kStages = kV4Stages;
+  constexpr int kTileBytes = kKT * kDh * 2;  // 8 KB
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kQBytes;
+  uint8_t* sV = sK + kStages * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * kTileBytes);
+  uint64_t* bar_kfull = bars;                 // [2] TMA K tile landed
+  uint64_t* bar_vfull = bars + kStages;       // [2] TMA V tile landed
+  uint64_t* bar_kempty = bars + 2 * kStages;  // [2] S(t) retired  -> K stage reusable
+  uint64_t* bar_vempty = bars + 3 * kStages;  // [2] PV(t) retired -> V stage reusable
+  uint64_t* bar_q = bars + 4 * kStages;
+  uint64_t* bar_s = bars + 4 * kStages + 1;   // S(t) ready - and, committed behind it, PV(t-1) retired
+  uint64_t* bar_p = bars + 4 * kStages + 2;   // P(t) written (128 softmax arrivals)
+  uint64_t* bar_done = bars + 4 * kStages + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kV4NumBars);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int N = p.N, H = p.H;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int m0 = blockIdx.x * kM;
+  const int ntiles = (N + kKT - 1) / kKT;
+  const int BHN = p.B * H * N;
+
+  if (warp == 4) {
+    if (tid == 128) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&bar_kfull[s], 1);
+        mbar_init(&bar_vfull[s], 1);
+        mbar_init(&bar_kempty[s], 1);
+        mbar_init(&bar_vempty[s], 1);
+      }
+      mbar_init(bar_q, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_done, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap);
+      mbar_expect_tx(bar_q, kQBytes);
+      tma_load_2d(sQ, &tmap, bar_q, 0, bh * N + m0);
+      tma_load_2d(sQ + kTileBytes, &tmap, bar_q, 0, bh * N + m0 + kKT);
+      for (int s = 0; s < kStages && s < ntiles; ++s) {
+        mbar_expect_tx(&bar_kfull[s], kTileBytes);
+        tma_load_2d(sK + s * kTileBytes, &tmap, &bar_kfull[s], 0, BHN + bh * N + s * kKT);
+      }
+      for (int s = 0; s < kStages && s < ntiles; ++s) {
+        mbar_expect_tx(&bar_vfull[s], kTileBytes);
+        tma_load_2d(sV + s * kTileBytes, &tmap, &bar_vfull[s], 0, 2 * BHN + bh * N + s * kKT);
+      }
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kV4TmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // =========================================== issuer ===========================================
+    const uint64_t desc_q = smem_desc_sw128(smem_u32(sQ));
+    constexpr uint32_t idesc_s = idesc_bf16(kM, kKT, 0, 0);
+    constexpr uint32_t idesc_o = idesc_bf16(kM, kDh, 0, 1);
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_kfull[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t desc_k = smem_desc_sw128(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < kDh / 16; ++k) mma_ss(tmem_base, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k > 0);
+      mma_commit(bar_s);
+      mma_commit(&bar_kempty[0]);
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; ++t) {
+      const int stage = t & 1;
+      const uint32_t use_parity = (uint32_t)((t >> 1) & 1);
+      // S(t) has been issued: once it retires its K stage takes K(t + 2); PV(t-1)'s V stage takes V(t + 1)
+      if (t + kStages < ntiles) {
+        mbar_wait(&bar_kempty[stage], use_parity);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_kfull[stage], kTileBytes);
+          tma_load_2d(sK + stage * kTileBytes, &tmap, &bar_kfull[stage], 0, BHN + bh * N + (t + kStages) * kKT);
+        }
+        __syncwarp();
+      }
+      if (t >= 1 && t + 1 < ntiles) {
+        const int sp = (t - 1) & 1;
+        mbar_wait(&bar_vempty[sp], (uint32_t)(((t - 1) >> 1) & 1));
+        if (elect_one()) {
+          mbar_expect_tx(&bar_vfull[sp], kTileBytes);
+          tma_load_2d(sV + sp * kTileBytes, &tmap, &bar_vfull[sp], 0, 2 * BHN + bh * N + (t + 1) * kKT);
+        }
+        __syncwarp();
+      }
+      // O += P(t) V(t), and S(t+1) right behind it into the columns P(t) occupies
+      mbar_wait(&bar_vfull[stage], use_parity);
+      if (t + 1 < ntiles) mbar_wait(&bar_kfull[(t + 1) & 1], (uint32_t)(((t + 1) >> 1) & 1));
+      mbar_wait(bar_p, (uint32_t)(t & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t desc_v = smem_desc_sw128(smem_u32(sV + stage * kTileBytes));
+        const int nvalid = min(kKT, N - t * kKT);
+        const int ksteps = (nvalid + 15) >> 4;
+        for (int kk = 0; kk < ksteps; ++kk)
+          mma_ts(tmem_base + kV4ColO, tmem_base + kk * 8, desc_v + 128 * kk, idesc_o, (t | kk) != 0);
+        mma_commit(&bar_vempty[stage]);
+        if (t + 1 < ntiles) {
+          const uint64_t desc_k = smem_desc_sw128(smem_u32(sK + ((t + 1) & 1) * kTileBytes));
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k) mma_ss(tmem_base, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k > 0);
+          mma_commit(bar_s);
+          mma_commit(&bar_kempty[(t + 1) & 1]);
+        } else {
+          mma_commit(bar_done);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================================== softmax ==========================================
+    const int i = m0 + tid;
+    const bool warp_active = (m0 + warp * 32) < N;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+      const int nvalid = min(kKT, N - t * kKT);
+      mbar_wait(bar_s, (uint32_t)(t & 1));
+      tc_fence_after();
+      if (warp_active) {
+        if (nvalid == kKT) v4_tile<true>(tmem_row, nvalid, t, p.scale_log2, p.rescale_threshold, m_ref, l_run);
+        else v4_tile<false>(tmem_row, nvalid, t, p.scale_log2, p.rescale_threshold, m_ref, l_run);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+
+    // ---- epilogue: O / l -------------------------------------------------------------------------
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    if (warp_active) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* dst = p.out + ((size_t)b * N + min(i, N - 1)) * (size_t)(H * kDh) + h * kDh;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        tmem_ld32(tmem_row + kV4ColO + half * 32, o);
+        tmem_wait_ld();
+        if (i < N) {
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(o[v8 * 8 + 0]) * inv, __uint_as_float(o[v8 * 8 + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(o[v8 * 8 + 2]) * inv, __uint_as_float(o[v8 * 8 + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(o[v8 * 8 + 4]) * inv, __uint_as_float(o[v8 * 8 + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(o[v8 * 8 + 6]) * inv, __uint_as_float(o[v8 * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + half * 32 + v8 * 8) = w;
+          }
+        }
+      }
+      if (i < N) p.lse[(size_t)bh * N + i] = (m_ref + log2f(l_run)) * kLn2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, kV4TmemCols);
+}
+
+constexpr size_t kFwd4SmemBytes = 1024 + (size_t)kQBytes + (size_t)2 * kV4Stages * kV2KT * kDh * 2 + (size_t)kV4NumBars * 8 + 16;
+
 size_t fwd2_smem_bytes(int N, const vrr_bias_desc* bias, int* lut_floats) {
   int lf = 0;
   if (bias && bias->mode == VRR_BIAS_TABLE) lf = 2 * N - 1 + 8;  // + slack for the aligned span
@@ -396,6 +681,7 @@ size_t fwd2_smem_bytes(int N, const vrr_bias_desc* bias, int* lut_floats) {
 }
 
 std::atomic<int> g_fwd_table_bulk{1};
+std::atomic<int> g_fwd_streams{4};  // 4: attn_fwd_tc4_kernel (four CTAs per SM); 2: attn_fwd_tc2_kernel
 std::atomic<int> g_fwd_thresh_x100{(int)(kRescaleThreshold * 100)};
 std::atomic<long long*> g_fwd_dbg{nullptr};
 
@@ -478,6 +764,7 @@ bool attn_fwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bia
 void attn_fwd_tc_set_debug(long long* buf) { g_fwd_dbg.store(buf); }
 void attn_fwd_tc_set_threshold_x100(int v) { g_fwd_thresh_x100.store(v); }
 void attn_fwd_tc_set_table_bulk(int v) { g_fwd_table_bulk.store(v); }
+void attn_fwd_tc_set_streams(int v) { g_fwd_streams.store(v == 2 ? 2 : 4); }
 
 template <int MODE>
 static int fwd2_launch_tc(const CUtensorMap& tmap, const FwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
@@ -510,6 +797,15 @@ int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float*
   if (mode == VRR_BIAS_TABLE)
     VRR_REQUIRE(((uintptr_t)bias->param & 15) == 0, VRR_ERR_INVALID_ARG, "attn_fwd (tcgen05): bias table must be 16-byte aligned");
   dim3 grid(ceil_div(N, kM), B * H);
+  if (g_fwd_streams.load() == 4 && mode == VRR_BIAS_NONE) {
+    // the bias modes stay on variant 2: evaluating the bias in both passes made the 4-CTA kernel slower there
+    // (577 tokens: table 118 vs 82 us, polynomial 175 vs 108 us)
+    p.lut_floats = 0;
+    VRR_SMEM_ATTR_ONCE(attn_fwd_tc4_kernel, 64 * 1024);
+    attn_fwd_tc4_kernel<<<grid, kV4Threads, kFwd4SmemBytes, st>>>(tmap, p);
+    VRR_LAUNCHED();
+    return VRR_OK;
+  }
   const size_t smem2 = fwd2_smem_bytes(N, bias, &p.lut_floats);
   if (mode == VRR_BIAS_TABLE) return fwd2_launch_tc<VRR_BIAS_TABLE>(tmap, p, grid, smem2, st);
   if (mode == VRR_BIAS_POLY) return fwd2_launch_tc<VRR_BIAS_POLY>(tmap, p, grid, smem2, st);

@@ -92,10 +92,10 @@ struct BiasEpilogue {
     if (sizeof(T) == 2) b = __bfloat162float(__float2bfloat16_rn(b));
     T r;
     Elem<T>::st(&r, v + b);
-    c[(long long)m * ldc + n] = r;
-    if (gelu) {
+    if (gelu != 2) c[(long long)m * ldc + n] = r;
+    if (gelu) {  // 1: c = h, c2 = gelu(h);  2: c = gelu(h) only (inference)
       const float h = Elem<T>::ld(&r);
-      Elem<T>::st(c2 + (long long)m * ldc + n, 0.5f * h * (1.f + erff(h * 0.70710678118654752f)));
+      Elem<T>::st((gelu == 2 ? c : c2) + (long long)m * ldc + n, 0.5f * h * (1.f + erff(h * 0.70710678118654752f)));
     }
   }
 };

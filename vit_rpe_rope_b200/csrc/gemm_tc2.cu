@@ -128,6 +128,7 @@ struct StoreEpi {
   int reduce;         // fp32 only: C += tile via TMA reduce-add (split-K partial sums / gradient accumulation)
   int gelu;           // bf16 only.  1: C = h = bf16(acc + bias), C2 = bf16(gelu(h)) (exact erf GELU);
                       //            2: C = bf16(gelu(h)), C2 = bf16(gelu'(h)) - what an Mlp backward needs instead of h
+                      //            3: C = bf16(gelu(h)) only (inference): one staging buffer, one TMA store
   const __nv_bfloat16* mul;  // bf16 only, or null: C = bf16(acc * mul[m][n]) (mul is [M][N] like C): d_act * gelu'(h)
 };
 
@@ -159,6 +160,24 @@ __device__ __forceinline__ void gelu_and_grad2(float2 h, float2& g, float2& dg) 
   const float2 cdf = make_float2(h.x >= 0.f ? om.x : q.x, h.y >= 0.f ? om.y : q.y);  // Phi(h)
   g = __fmul2_rn(h, cdf);
   dg = __ffma2_rn(__fmul2_rn(h, e), make_float2(0.3989422804014327f, 0.3989422804014327f), cdf);
+}
+
+// gelu(h) alone, packed to bf16x2 (same Phi(h) as above)
+__device__ __forceinline__ uint32_t gelu_only2(float2 h) {
+  const float2 hh = __fmul2_rn(h, h);
+  const float2 ea = __fmul2_rn(hh, make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  const float2 e = make_float2(ex2(ea.x), ex2(ea.y));
+  const float2 za = make_float2(fabsf(h.x), fabsf(h.y));
+  const float2 den = __ffma2_rn(za, make_float2(0.23164190f, 0.23164190f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 poly = __ffma2_rn(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+  poly = __ffma2_rn(poly, t, make_float2(0.7107068705f, 0.7107068705f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.142248368f, -0.142248368f));
+  poly = __ffma2_rn(poly, t, make_float2(0.127414796f, 0.127414796f));
+  const float2 q = __fmul2_rn(__fmul2_rn(poly, t), e);
+  const float2 om = __ffma2_rn(q, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  const float2 g = __fmul2_rn(h, make_float2(h.x >= 0.f ? om.x : q.x, h.y >= 0.f ? om.y : q.y));
+  return pack_bf16(g.x, g.y);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -380,6 +399,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   const uint32_t hw = pack_bf16(hs.x, hs.y);
                   const float2 hr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));  // h as stored
                   float2 gl, dg;
+                  if (epi.gelu == 3) {
+                    o0[c8 * 4 + j] = gelu_only2(hr);
+                    continue;
+                  }
                   gelu_and_grad2(hr, gl, dg);
                   if (epi.gelu == 1) {
                     o0[c8 * 4 + j] = hw;
@@ -396,14 +419,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int c8 = 0; c8 < 8; ++c8) {
                 const uint32_t off = (((uint32_t)c8 ^ sw) << 4);
                 st_shared_v4(row_base + off, o0[c8 * 4], o0[c8 * 4 + 1], o0[c8 * 4 + 2], o0[c8 * 4 + 3]);
-                st_shared_v4(row_base + 4096u + off, o1[c8 * 4], o1[c8 * 4 + 1], o1[c8 * 4 + 2], o1[c8 * 4 + 3]);
+                if (epi.gelu != 3)
+                  st_shared_v4(row_base + 4096u + off, o1[c8 * 4], o1[c8 * 4 + 1], o1[c8 * 4 + 2], o1[c8 * 4 + 3]);
               }
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
                 if (store_ok) {
                   tma_store_2d(&tmap_c, my_stage, n0, m_warp0);
-                  tma_store_2d(&tmap_c2, my_stage + 4096, n0, m_warp0);
+                  if (epi.gelu != 3) tma_store_2d(&tmap_c2, my_stage + 4096, n0, m_warp0);
                 }
                 bulk_commit();
               }
@@ -559,7 +583,7 @@ int launch_store(const void* a, const void* b, void* c, void* c2, const float* b
   StoreEpi epi;
   epi.bias = (epilogue != VRR_EPI_NONE && epilogue != VRR_EPI_MUL) ? bias : nullptr;
   epi.out_f32 = c_f32;
-  epi.gelu = epilogue == VRR_EPI_BIAS_GELU ? 1 : (epilogue == VRR_EPI_BIAS_GELU_GRAD ? 2 : 0);
+  epi.gelu = epilogue == VRR_EPI_BIAS_GELU ? 1 : (epilogue == VRR_EPI_BIAS_GELU_GRAD ? 2 : (epilogue == VRR_EPI_BIAS_GELU_ACT ? 3 : 0));
   epi.mul = epilogue == VRR_EPI_MUL ? (const __nv_bfloat16*)c2 : nullptr;
   if (epilogue == VRR_EPI_MUL) epi.bias = nullptr;
   const int tiles = ceil_div(M, 2 * kPM) * ceil_div(N, N > 128 ? 256 : 128);
@@ -574,7 +598,7 @@ int launch_store(const void* a, const void* b, void* c, void* c2, const float* b
   } else {
     if (int rc = make_tmap_2d(&tc_, c, 2, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64)) return rc;
     tc2_ = tc_;
-    if (epi.gelu)
+    if (epi.gelu == 1 || epi.gelu == 2)
       if (int rc = make_tmap_2d(&tc2_, c2, 2, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64)) return rc;
   }
   if (N > 128) return launch_pair<256, A_MN, B_MN, StoreEpi>(a, b, M, N, K, splits, tc_, tc2_, epi, st);
@@ -608,8 +632,8 @@ int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* b
               "gemm (tcgen05): a / b / c must be 16-byte aligned");
   VRR_REQUIRE(epilogue == VRR_EPI_NONE || epilogue == VRR_EPI_MUL || (bias != nullptr && ((uintptr_t)bias & 15) == 0),
               VRR_ERR_INVALID_ARG, "gemm (tcgen05): the bias epilogues need a 16-byte aligned fp32 bias");
-  VRR_REQUIRE(epilogue < VRR_EPI_BIAS_GELU || c2 != nullptr, VRR_ERR_INVALID_ARG,
-              "gemm (tcgen05): the GELU / MUL epilogues need c2");
+  VRR_REQUIRE(epilogue < VRR_EPI_BIAS_GELU || epilogue == VRR_EPI_BIAS_GELU_ACT || c2 != nullptr, VRR_ERR_INVALID_ARG,
+              "gemm (tcgen05): the two-output GELU epilogues and MUL need c2");
   VRR_REQUIRE(!accumulate || c_dtype == VRR_F32, VRR_ERR_UNSUPPORTED, "gemm (tcgen05): accumulate needs an fp32 C");
   const int c_f32 = c_dtype == VRR_F32;
   const bool a_mn = trans_a != 0, b_mn = trans_b == 0;

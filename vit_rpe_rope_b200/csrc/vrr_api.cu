@@ -149,6 +149,7 @@ int vrr_set_option(const char* name, int value) {
   if (!strcmp(name, "ln_bwd_minb")) { layernorm_set_option(1, value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_variant")) { g_attn_fwd_variant.store(value); return VRR_OK; }
   if (!strcmp(name, "attn_bwd_variant")) { g_attn_bwd_variant.store(value); return VRR_OK; }
+  if (!strcmp(name, "attn_fwd_streams")) { attn_fwd_tc_set_streams(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_rescale_threshold_x100")) {
     attn_fwd_tc_set_threshold_x100(value);
@@ -292,10 +293,12 @@ int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bi
   VRR_REQUIRE(a && b && c, VRR_ERR_INVALID_ARG, "gemm_ex: NULL pointer");
   VRR_REQUIRE(M > 0 && N > 0 && K > 0, VRR_ERR_INVALID_ARG, "gemm_ex: bad sizes");
   VRR_REQUIRE(dtype_ok(dtype) && dtype_ok(c_dtype), VRR_ERR_INVALID_ARG, "gemm_ex: bad dtype %d/%d", dtype, c_dtype);
-  VRR_REQUIRE(epilogue >= VRR_EPI_NONE && epilogue <= VRR_EPI_MUL, VRR_ERR_INVALID_ARG, "gemm_ex: bad epilogue %d", epilogue);
+  VRR_REQUIRE(epilogue >= VRR_EPI_NONE && epilogue <= VRR_EPI_BIAS_GELU_ACT, VRR_ERR_INVALID_ARG, "gemm_ex: bad epilogue %d",
+              epilogue);
   VRR_REQUIRE(epilogue == VRR_EPI_NONE || epilogue == VRR_EPI_MUL || bias, VRR_ERR_INVALID_ARG,
               "gemm_ex: the bias epilogues need `bias`");
-  VRR_REQUIRE(epilogue < VRR_EPI_BIAS_GELU || c2, VRR_ERR_INVALID_ARG, "gemm_ex: the GELU / MUL epilogues need `c2`");
+  VRR_REQUIRE(epilogue < VRR_EPI_BIAS_GELU || epilogue == VRR_EPI_BIAS_GELU_ACT || c2, VRR_ERR_INVALID_ARG,
+              "gemm_ex: the two-output GELU epilogues and MUL need `c2`");
   if (int rc = require_device()) return rc;
   const int impl = g_impl.load();
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && gemm_bf16_tc_supported(M, N, K, trans_a, trans_b, c_dtype, epilogue)) {
@@ -318,8 +321,8 @@ int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bi
       if (int rc = gemm_simt_bias(a, b, c2, c, bias, M, N, K, trans_a, trans_b, dtype, 1, (cudaStream_t)stream)) return rc;
       return gelu_grad_inplace(c2, (size_t)M * N, dtype, (cudaStream_t)stream);
     }
-    return gemm_simt_bias(a, b, c, c2, bias, M, N, K, trans_a, trans_b, dtype, epilogue == VRR_EPI_BIAS_GELU,
-                          (cudaStream_t)stream);
+    return gemm_simt_bias(a, b, c, c2, bias, M, N, K, trans_a, trans_b, dtype,
+                          epilogue == VRR_EPI_BIAS_GELU ? 1 : (epilogue == VRR_EPI_BIAS_GELU_ACT ? 2 : 0), (cudaStream_t)stream);
   }
   return gemm_simt(a, b, c, M, N, K, trans_a, trans_b, dtype, c_dtype, (cudaStream_t)stream);
 }

@@ -271,7 +271,7 @@ def _gemm(a, b, trans_a, trans_b, out_dtype, bias=None, epilogue=_lib.EPI_NONE, 
     run the tcgen05 CTA-pair kernel (fp32 accumulation; result in ``out_dtype``: bf16, or fp32 for weight
     gradients), fp32 operands the exact-fp32 FFMA kernel (no TF32).  ``epilogue``: fused ``+ bias`` or
     ``+ bias, GELU`` (``out2``: second output - gelu(C) for EPI_BIAS_GELU; EPI_BIAS_GELU_GRAD returns
-    (gelu(h), gelu'(h)) instead); ``aux``: the [M][N] multiplier of EPI_MUL."""
+    (gelu(h), gelu'(h)) instead; EPI_BIAS_GELU_ACT returns gelu(h) alone); ``aux``: the [M][N] multiplier of EPI_MUL."""
     lib = _lib.load()
     M = a.shape[1] if trans_a else a.shape[0]
     K = a.shape[0] if trans_a else a.shape[1]
@@ -534,6 +534,10 @@ class MlpFn(torch.autograd.Function):
         w1l = (w1_lp if w1_lp is not None else w1.detach().to(dt)).detach()
         w2l = (w2_lp if w2_lp is not None else w2.detach().to(dt)).detach()
         x2 = x.reshape(-1, x.shape[-1])
+        if not any(ctx.needs_input_grad):  # inference: the activation alone - one output stream instead of two
+            a = _gemm(x2, w1l, False, True, dt, bias=b1, epilogue=_lib.EPI_BIAS_GELU_ACT, name="fc1_fwd")
+            y = _gemm(a, w2l, False, True, dt, bias=b2, epilogue=_lib.EPI_BIAS, name="fc2_fwd")
+            return y.view(*x.shape[:-1], w2l.shape[0])
         a, gp = _gemm(x2, w1l, False, True, dt, bias=b1, epilogue=_lib.EPI_BIAS_GELU_GRAD, out2=True, name="fc1_fwd")
         y = _gemm(a, w2l, False, True, dt, bias=b2, epilogue=_lib.EPI_BIAS, name="fc2_fwd")
         ctx.save_for_backward(x2, gp, a, w1l, w2l)
