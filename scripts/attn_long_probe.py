@@ -68,8 +68,9 @@ def timeit(b, h, n, kind="none", reps=10):
     prm = None if param is None else param.to(DEV)
     flush = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
     res = {}
-    for streams in (2, 4):
-        setopt("attn_fwd_streams", streams)
+    for streams in (2, 4, 40, 41, 43, 44):  # 4x = four CTAs per SM with x of 8 exponential pairs by polynomial
+        setopt("attn_fwd_streams", 2 if streams == 2 else 4)
+        setopt("attn_fwd_poly_exp", streams - 40 if streams >= 40 else 2)
         for _ in range(3):
             ops.fused_attention(planes, d ** -0.5, mode, prm, grid)
         tot = 0.0
@@ -84,7 +85,9 @@ def timeit(b, h, n, kind="none", reps=10):
         res[streams] = tot / reps * 1e3
     fl = 4.0 * b * h * n * n * d
     print(f"B={b} H={h} N={n} {kind:6s}: 2-CTA {res[2]:7.1f} us ({fl / res[2] / 1e6:5.0f} TF)   4-CTA {res[4]:7.1f} us "
-          f"({fl / res[4] / 1e6:5.0f} TF)   x{res[2] / res[4]:.2f}", flush=True)
+          f"({fl / res[4] / 1e6:5.0f} TF)   x{res[2] / res[4]:.2f}   poly 0/1/3/4 of 8: "
+          + " ".join(f"{res[k]:.1f}" for k in (40, 41, 43, 44)), flush=True)
+    setopt("attn_fwd_poly_exp", 2)
 
 
 ok = True

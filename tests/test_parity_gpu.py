@@ -693,6 +693,29 @@ def test_attention_kernel_variants_agree(n):
     assert err_rel(res[3][1], res[2][1].cpu().numpy()) <= BF16_TOL
 
 
+@pytest.mark.parametrize("b,h,n", [(2, 3, 257), (1, 2, 577), (3, 2, 641), (1, 2, 1025)])
+def test_long_sequence_forward_variants_vs_oracle(b, h, n):
+    """N > 256 without bias: the four-CTAs-per-SM forward (single S buffer, chunked TMEM re-reads, a share of the
+    exponentials by polynomial on the FMA pipe) at polynomial shares 0, 2 (default) and 4 of 8, and the two-CTA
+    kernel, each against the float64 numpy oracle; ragged last key tile (n % 64 = 1) and ragged last row tile."""
+    d = 64
+    planes = _planes(b, h, n, d, torch.bfloat16, seed=41).to(DEV)
+    pl = planes.double().cpu().numpy()
+    want, _, _, _ = A.attention_forward(pl[0], pl[1], pl[2], d ** -0.5, None)  # [B, N, H*D]
+    try:
+        for streams, poly in ((4, 0), (4, 2), (4, 4), (2, 2)):
+            _set_option("attn_fwd_streams", streams)
+            _set_option("attn_fwd_poly_exp", poly)
+            with tcgen05_must_run():
+                out = ops.fused_attention(planes, d ** -0.5)
+            e = err_rel(out.float(), want)
+            report(f"long forward b={b} h={h} n={n} streams={streams} poly={poly}: err {e:.2e}")
+            assert e <= 1e-2, (streams, poly, e)
+    finally:
+        _set_option("attn_fwd_streams", 4)
+        _set_option("attn_fwd_poly_exp", 2)
+
+
 @pytest.mark.parametrize("m,n,k", [(394, 3072, 768), (130, 104, 72), (1000, 256, 520)])
 def test_gemm_epilogues_gelu_grad_and_mul(m, n, k):
     """VRR_EPI_BIAS_GELU_GRAD (c = gelu(h), c2 = gelu'(h), h = bf16(a.b^T + bias)) and VRR_EPI_MUL (c = (a.b) * c2),

@@ -415,14 +415,36 @@ __device__ __forceinline__ float v4_max16m(const uint32_t (&r)[16], float mx, in
     return mx;
   }
 }
-// P = 2^(s * scale - m) for 16 scores -> 8 packed bf16x2; the row sum accumulates in l2
-template <bool FULL>
+// 2^x for two values WITHOUT the MUFU unit: x = n + f with n = round(x) (magic-number add), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5 - P is rounded to bf16, 3.9e-3, right after) and n
+// added into the exponent field.  ~5 FMA-pipe instructions per value on the packed fp32x2 pipe: MUFU.EX2 issues 16
+// per clock per SM against 32 softmax elements per clock the tensor pipe could consume at head dim 64, so a share
+// of the exponentials computed here raises the kernel's MUFU-bound ceiling.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x = make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f));
+  const float2 magic = make_float2(12582912.f, 12582912.f);  // 1.5 * 2^23: the integer lands in the low mantissa bits
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 q = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), f, make_float2(0.2426111251f, 0.2426111251f));
+  q = __ffma2_rn(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = __ffma2_rn(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  // (bits(t) << 23) == (n << 23) modulo 2^32: the magic constant's low nine bits are zero
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+
+// P = 2^(s * scale - m) for 16 scores -> 8 packed bf16x2; the row sum accumulates in l2.  POLY of the 8 pairs take
+// the polynomial, the others MUFU.EX2.
+template <bool FULL, int POLY>
 __device__ __forceinline__ void v4_exp16(const uint32_t (&r)[16], uint32_t (&pk)[8], float2 sc2, float2 nm2, float2& l2,
                                          int first, int nvalid) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2);
-    float2 pv = make_float2(ex2(x.x), ex2(x.y));
+    // spread the polynomial pairs between the MUFU ones: e * POLY / 8 steps at the chosen pairs
+    const bool poly = ((e + 1) * POLY) / 8 != (e * POLY) / 8;
+    float2 pv = poly ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
     if (!FULL) {
       if (first + 2 * e >= nvalid) pv.x = 0.f;
       if (first + 2 * e + 1 >= nvalid) pv.y = 0.f;
@@ -433,25 +455,23 @@ __device__ __forceinline__ void v4_exp16(const uint32_t (&r)[16], uint32_t (&pk)
 }
 
 // one key tile of one query row: lazy reference-max update, then P over the first 32 of the 64 columns S occupied
-template <bool FULL>
+template <bool FULL, int POLY>
 __device__ __forceinline__ void v4_tile(uint32_t trow, int nvalid, int t, float scale_log2, float thr, float& m_ref,
                                         float& l_run) {
-  uint32_t a[16], b[16];
-  // ---- pass 1: tile max ----
+  uint32_t ab[32];
+  uint32_t(&a)[16] = *reinterpret_cast<uint32_t(*)[16]>(&ab[0]);
+  uint32_t(&b)[16] = *reinterpret_cast<uint32_t(*)[16]>(&ab[16]);
+  // ---- pass 1: tile max (two 32-column loads: one TMEM round trip less than four 16-column ones) ----
   float tmax = -INFINITY;
-  tmem_ld16(trow, a);
+  tmem_ld32(trow, ab);
   tmem_wait_ld();
-  tmem_ld16(trow + 16, b);
   tmax = v4_max16m<FULL>(a, tmax, 0, nvalid);
-  tmem_wait_ld();
-  tmem_ld16(trow + 32, a);
   tmax = v4_max16m<FULL>(b, tmax, 16, nvalid);
+  tmem_ld32(trow + 32, ab);
   tmem_wait_ld();
-  tmem_ld16(trow + 48, b);
   tmax = v4_max16m<FULL>(a, tmax, 32, nvalid);
-  tmem_wait_ld();
-  tmem_ld16(trow, a);  // first chunk of pass 2
   tmax = v4_max16m<FULL>(b, tmax, 48, nvalid) * scale_log2;
+  tmem_ld16(trow, a);  // first chunk of pass 2
   const bool jump = tmax > m_ref + thr;
   if (__any_sync(0xffffffffu, jump)) {
     const float m_new = fmaxf(m_ref, tmax);
@@ -477,23 +497,24 @@ __device__ __forceinline__ void v4_tile(uint32_t trow, int nvalid, int t, float 
   uint32_t pk[8];
   tmem_wait_ld();
   tmem_ld16(trow + 16, b);
-  v4_exp16<FULL>(a, pk, sc2, nm2, l2, 0, nvalid);
+  v4_exp16<FULL, POLY>(a, pk, sc2, nm2, l2, 0, nvalid);
   tmem_st8(trow, pk);  // columns [0,8): scores already consumed
   tmem_wait_ld();
   tmem_ld16(trow + 32, a);
-  v4_exp16<FULL>(b, pk, sc2, nm2, l2, 16, nvalid);
+  v4_exp16<FULL, POLY>(b, pk, sc2, nm2, l2, 16, nvalid);
   tmem_st8(trow + 8, pk);
   tmem_wait_ld();
   tmem_ld16(trow + 48, b);
-  v4_exp16<FULL>(a, pk, sc2, nm2, l2, 32, nvalid);
+  v4_exp16<FULL, POLY>(a, pk, sc2, nm2, l2, 32, nvalid);
   tmem_st8(trow + 16, pk);
   tmem_wait_ld();
-  v4_exp16<FULL>(b, pk, sc2, nm2, l2, 48, nvalid);
+  v4_exp16<FULL, POLY>(b, pk, sc2, nm2, l2, 48, nvalid);
   tmem_st8(trow + 24, pk);
   l_run += l2.x + l2.y;
   tmem_wait_st();
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(kV4Threads, 4)
 attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
   constexpr int kKT = kV2KT, kStages = kV4Stages;
@@ -531,7 +552,7 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p)
       }
       mbar_init(bar_q, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128);
+      mbar_init(bar_p, 4);  // one elected lane per softmax warp
       mbar_init(bar_done, 1);
       fence_mbar_init();
     }
@@ -630,11 +651,12 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p)
       mbar_wait(bar_s, (uint32_t)(t & 1));
       tc_fence_after();
       if (warp_active) {
-        if (nvalid == kKT) v4_tile<true>(tmem_row, nvalid, t, p.scale_log2, p.rescale_threshold, m_ref, l_run);
-        else v4_tile<false>(tmem_row, nvalid, t, p.scale_log2, p.rescale_threshold, m_ref, l_run);
+        if (nvalid == kKT) v4_tile<true, POLY>(tmem_row, nvalid, t, p.scale_log2, p.rescale_threshold, m_ref, l_run);
+        else v4_tile<false, POLY>(tmem_row, nvalid, t, p.scale_log2, p.rescale_threshold, m_ref, l_run);
       }
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (elect_one()) mbar_arrive(bar_p);
     }
 
     // ---- epilogue: O / l -------------------------------------------------------------------------
@@ -681,6 +703,7 @@ size_t fwd2_smem_bytes(int N, const vrr_bias_desc* bias, int* lut_floats) {
 }
 
 std::atomic<int> g_fwd_table_bulk{1};
+std::atomic<int> g_fwd_poly{2};     // pairs out of 8 whose exponential the 4-CTA kernel computes by polynomial (0..4)
 std::atomic<int> g_fwd_streams{4};  // 4: attn_fwd_tc4_kernel (four CTAs per SM); 2: attn_fwd_tc2_kernel
 std::atomic<int> g_fwd_thresh_x100{(int)(kRescaleThreshold * 100)};
 std::atomic<long long*> g_fwd_dbg{nullptr};
@@ -765,6 +788,7 @@ void attn_fwd_tc_set_debug(long long* buf) { g_fwd_dbg.store(buf); }
 void attn_fwd_tc_set_threshold_x100(int v) { g_fwd_thresh_x100.store(v); }
 void attn_fwd_tc_set_table_bulk(int v) { g_fwd_table_bulk.store(v); }
 void attn_fwd_tc_set_streams(int v) { g_fwd_streams.store(v == 2 ? 2 : 4); }
+void attn_fwd_tc_set_poly(int v) { g_fwd_poly.store(v < 0 ? 0 : (v > 4 ? 4 : v)); }
 
 template <int MODE>
 static int fwd2_launch_tc(const CUtensorMap& tmap, const FwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
@@ -801,8 +825,18 @@ int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float*
     // the bias modes stay on variant 2: evaluating the bias in both passes made the 4-CTA kernel slower there
     // (577 tokens: table 118 vs 82 us, polynomial 175 vs 108 us)
     p.lut_floats = 0;
-    VRR_SMEM_ATTR_ONCE(attn_fwd_tc4_kernel, 64 * 1024);
-    attn_fwd_tc4_kernel<<<grid, kV4Threads, kFwd4SmemBytes, st>>>(tmap, p);
+    switch (g_fwd_poly.load()) {
+#define VRR_FWD4(P)                                                              \
+  case P:                                                                        \
+    VRR_SMEM_ATTR_ONCE(attn_fwd_tc4_kernel<P>, 64 * 1024);                       \
+    attn_fwd_tc4_kernel<P><<<grid, kV4Threads, kFwd4SmemBytes, st>>>(tmap, p);   \
+    break;
+      VRR_FWD4(0) VRR_FWD4(1) VRR_FWD4(2) VRR_FWD4(3) VRR_FWD4(4)
+#undef VRR_FWD4
+      default:
+        VRR_SMEM_ATTR_ONCE(attn_fwd_tc4_kernel<2>, 64 * 1024);
+        attn_fwd_tc4_kernel<2><<<grid, kV4Threads, kFwd4SmemBytes, st>>>(tmap, p);
+    }
     VRR_LAUNCHED();
     return VRR_OK;
   }

@@ -128,7 +128,7 @@ struct StoreEpi {
   int reduce;         // fp32 only: C += tile via TMA reduce-add (split-K partial sums / gradient accumulation)
   int gelu;           // bf16 only.  1: C = h = bf16(acc + bias), C2 = bf16(gelu(h)) (exact erf GELU);
                       //            2: C = bf16(gelu(h)), C2 = bf16(gelu'(h)) - what an Mlp backward needs instead of h
-                      //            3: C = bf16(gelu(h)) only (inference): one staging buffer, one TMA store
+                      //            3: C = bf16(gelu(h)) only (inference): its own code path, one TMA store per chunk
   const __nv_bfloat16* mul;  // bf16 only, or null: C = bf16(acc * mul[m][n]) (mul is [M][N] like C): d_act * gelu'(h)
 };
 
@@ -382,7 +382,38 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t row_base = stage_u32 + (uint32_t)lane * 128u;
           if (!epi.out_f32) {
             // ---- bf16 C ----
-            if (epi.gelu != 0) {
+            if (epi.gelu == 3) {
+              // inference: gelu(h) alone.  Its own branch - folding it into the two-output code below cost that path
+              // 50 us per launch (register allocation of the o0 / o1 arrays).
+              uint32_t o0[32];
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                const int nb = min(n0 + c8 * 8, g.N - 8);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb + 4));
+                const uint32_t br[4] = {pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&br[j]));
+                  const float2 hs = __fadd2_rn(make_float2(f[c8 * 8 + 2 * j], f[c8 * 8 + 2 * j + 1]), bb);
+                  const uint32_t hw = pack_bf16(hs.x, hs.y);
+                  o0[c8 * 4 + j] = gelu_only2(__bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw)));
+                }
+              }
+              const uint32_t buf = (chunk_counter & 1u) * 4096u;
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8)
+                st_shared_v4(row_base + buf + (((uint32_t)c8 ^ sw) << 4), o0[c8 * 4], o0[c8 * 4 + 1], o0[c8 * 4 + 2],
+                             o0[c8 * 4 + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (store_ok) tma_store_2d(&tmap_c, my_stage + buf, n0, m_warp0);
+                bulk_commit();
+              }
+            } else if (epi.gelu != 0) {
               // two outputs: (h, gelu(h)) or (gelu(h), gelu'(h)).  The chunk is computed into registers FIRST and only
               // then waits for the previous chunk's TMA stores to release the two staging buffers.
               uint32_t o0[32], o1[32];
@@ -399,10 +430,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   const uint32_t hw = pack_bf16(hs.x, hs.y);
                   const float2 hr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));  // h as stored
                   float2 gl, dg;
-                  if (epi.gelu == 3) {
-                    o0[c8 * 4 + j] = gelu_only2(hr);
-                    continue;
-                  }
                   gelu_and_grad2(hr, gl, dg);
                   if (epi.gelu == 1) {
                     o0[c8 * 4 + j] = hw;
@@ -419,15 +446,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int c8 = 0; c8 < 8; ++c8) {
                 const uint32_t off = (((uint32_t)c8 ^ sw) << 4);
                 st_shared_v4(row_base + off, o0[c8 * 4], o0[c8 * 4 + 1], o0[c8 * 4 + 2], o0[c8 * 4 + 3]);
-                if (epi.gelu != 3)
-                  st_shared_v4(row_base + 4096u + off, o1[c8 * 4], o1[c8 * 4 + 1], o1[c8 * 4 + 2], o1[c8 * 4 + 3]);
+                st_shared_v4(row_base + 4096u + off, o1[c8 * 4], o1[c8 * 4 + 1], o1[c8 * 4 + 2], o1[c8 * 4 + 3]);
               }
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
                 if (store_ok) {
                   tma_store_2d(&tmap_c, my_stage, n0, m_warp0);
-                  if (epi.gelu != 3) tma_store_2d(&tmap_c2, my_stage + 4096, n0, m_warp0);
+                  tma_store_2d(&tmap_c2, my_stage + 4096, n0, m_warp0);
                 }
                 bulk_commit();
               }

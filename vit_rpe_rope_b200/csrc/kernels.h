@@ -17,6 +17,7 @@ int attn_bwd_simt(const void* planes, const vrr_bias_desc* bias, const void* out
 bool attn_fwd_tc_supported(int B, int H, int N, int Dh, const vrr_bias_desc* bias);
 void attn_fwd_tc_set_threshold_x100(int v);
 void attn_fwd_tc_set_table_bulk(int v);
+void attn_fwd_tc_set_poly(int v);     // 0..4 of every 8 exponential pairs by polynomial in attn_fwd_tc4_kernel
 void attn_fwd_tc_set_streams(int v);  // 4 (default): attn_fwd_tc4_kernel, four CTAs per SM; 2: attn_fwd_tc2_kernel
 void attn_fwd_tc_set_debug(long long* buf);
 int attn_fwd_tc(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,

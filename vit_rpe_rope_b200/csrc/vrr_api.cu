@@ -149,6 +149,7 @@ int vrr_set_option(const char* name, int value) {
   if (!strcmp(name, "ln_bwd_minb")) { layernorm_set_option(1, value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_variant")) { g_attn_fwd_variant.store(value); return VRR_OK; }
   if (!strcmp(name, "attn_bwd_variant")) { g_attn_bwd_variant.store(value); return VRR_OK; }
+  if (!strcmp(name, "attn_fwd_poly_exp")) { attn_fwd_tc_set_poly(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_streams")) { attn_fwd_tc_set_streams(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_table_bulk")) { attn_fwd_tc_set_table_bulk(value); return VRR_OK; }
   if (!strcmp(name, "attn_fwd_rescale_threshold_x100")) {
