@@ -505,7 +505,7 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else int(out.numel() * 4)},
         "gpu_launches": int(gpu_launches),
         "roofline": roofline, "rooflines": rooflines, "hot_path_kernels": extra, "model_tflops": step_tflops,
-        "mfu_vs_bf16_sustained": step_tflops / peaks["bf16_tflops_sustained"] if bf16 else None,
+        "mfu_vs_bf16_sustained": step_tflops / (world * peaks["bf16_tflops_sustained"]) if bf16 else None,
         "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu, "clocks": clocks, "last_result": last,
     }
     print(json.dumps(line), flush=True)
