@@ -693,6 +693,45 @@ def test_attention_kernel_variants_agree(n):
     assert err_rel(res[3][1], res[2][1].cpu().numpy()) <= BF16_TOL
 
 
+@pytest.mark.parametrize("rope", ["axial", "mixed"])
+@pytest.mark.parametrize("b,n,e,h", [(3, 197, 768, 12), (2, 50, 128, 2), (5, 65, 192, 3)])
+def test_qkv_rope_packed_tables_bit_identical(rope, b, n, e, h):
+    """vrr_rope_pack_tables + vrr_qkv_rope_fwd_packed (coalesced table reads in the tcgen05 epilogue) against
+    vrr_qkv_rope_fwd on the same inputs: bit-identical planes; and the Python-side cache notices a table that changed
+    in place."""
+    lib = _lib.load()
+    dh = e // h
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(b, n, e, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(3 * e, e, generator=g) * e ** -0.5).to(torch.bfloat16).to(DEV)
+    heads = h if rope == "mixed" else 1
+    ang = torch.rand(heads, n - 1, dh // 2, generator=g) * 6.0
+    cos, sin = torch.cos(ang).to(DEV), torch.sin(ang).to(DEV)
+    mode = _lib.ROPE_MIXED if rope == "mixed" else _lib.ROPE_AXIAL
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    plain = torch.empty(3, b, h, n, dh, device=DEV, dtype=torch.bfloat16)
+    fast = torch.empty_like(plain)
+    packed = torch.empty(heads, dh // 4, n - 1, 4, device=DEV)
+    with tcgen05_must_run():
+        _lib.check(lib.vrr_qkv_rope_fwd(p(x), p(w), p(cos), p(sin), p(plain), b, n, e, h, mode, 1, st), "plain")
+    _lib.check(lib.vrr_rope_pack_tables(p(cos), p(sin), p(packed), heads, n - 1, dh // 2, st), "pack")
+    want = torch.stack([cos[..., 0::2], sin[..., 0::2], cos[..., 1::2], sin[..., 1::2]], dim=-1).permute(0, 2, 1, 3)
+    assert torch.equal(packed, want.contiguous())
+    with tcgen05_must_run():
+        _lib.check(lib.vrr_qkv_rope_fwd_packed(p(x), p(w), p(cos), p(sin), p(packed), p(fast), b, n, e, h, mode, 1, st), "packed")
+    assert torch.equal(plain, fast)
+    # host mirror: same storage + same version -> cached; an in-place change -> repacked
+    cs = cos if rope == "mixed" else cos[0]
+    sn = sin if rope == "mixed" else sin[0]
+    out1 = ops.QkvRopeFn.apply(x, w, cs, sn, h)
+    assert torch.equal(out1, plain)
+    cs.mul_(-1.0)
+    out2 = ops.QkvRopeFn.apply(x, w, cs, sn, h)
+    _lib.check(lib.vrr_qkv_rope_fwd(p(x), p(w), p(cos), p(sin), p(plain), b, n, e, h, mode, 1, st), "plain")
+    assert torch.equal(out2, plain) and not torch.equal(out1, out2)
+
+
 @pytest.mark.parametrize("b,h,n", [(2, 3, 257), (1, 2, 577), (3, 2, 641), (1, 2, 1025)])
 def test_long_sequence_forward_variants_vs_oracle(b, h, n):
     """N > 256 without bias: the four-CTAs-per-SM forward (single S buffer, chunked TMEM re-reads, a share of the

@@ -58,12 +58,25 @@ struct QkvRopeEpi2 {
   static constexpr bool kPlaneStore = true;
   __nv_bfloat16* planes;
   const float *cos_tab, *sin_tab;
+  const float4* packed;  // rope_pack_tables layout [heads][16][N-1], or null
   int B, N, E, H, rope_mode;
   __device__ __forceinline__ void rotate(int m, int n0, float (&f)[64]) const {
     const int hd = 32;
     const int b = m / N, t = m - b * N;
     const int which = n0 / E, h = (n0 - which * E) >> 6;
-    if (rope_mode != VRR_ROPE_NONE && which < 2 && t >= 1 && b < B) {
+    if (rope_mode != VRR_ROPE_NONE && which < 2 && t >= 1 && b < B && packed != nullptr) {
+      // lanes = consecutive token rows = consecutive float4 of the packed table: coalesced 512-byte requests
+      const float4* pk = packed + (size_t)(rope_mode == VRR_ROPE_MIXED ? h * 16 : 0) * (N - 1) + (t - 1);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 v = __ldg(pk + (size_t)q * (N - 1));  // {cos[2q], sin[2q], cos[2q+1], sin[2q+1]}
+        const float x1 = f[2 * q], x2 = f[2 * q + hd], y1 = f[2 * q + 1], y2 = f[2 * q + 1 + hd];
+        f[2 * q] = x1 * v.x - x2 * v.y;
+        f[2 * q + hd] = x1 * v.y + x2 * v.x;
+        f[2 * q + 1] = y1 * v.z - y2 * v.w;
+        f[2 * q + 1 + hd] = y1 * v.w + y2 * v.z;
+      }
+    } else if (rope_mode != VRR_ROPE_NONE && which < 2 && t >= 1 && b < B) {
       const size_t base = ((size_t)(rope_mode == VRR_ROPE_MIXED ? h * (N - 1) : 0) + (t - 1)) * hd;
       const float4* c4 = reinterpret_cast<const float4*>(cos_tab + base);
       const float4* s4 = reinterpret_cast<const float4*>(sin_tab + base);
@@ -670,14 +683,15 @@ int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* b
 }
 
 // ---- QKV projection + RoPE epilogue on the CTA-pair kernel -----------------------------------------------
-int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes, int B, int N,
-                     int E, int H, int rope_mode, cudaStream_t st) {
+int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const float* sin_tab, const float* packed,
+                     void* planes, int B, int N, int E, int H, int rope_mode, cudaStream_t st) {
   VRR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)planes & 15) == 0,
               VRR_ERR_INVALID_ARG, "qkv_rope_fwd (tcgen05): x / w / planes must be 16-byte aligned");
   if (rope_mode != VRR_ROPE_NONE)
     VRR_REQUIRE(((uintptr_t)cos_tab & 15) == 0 && ((uintptr_t)sin_tab & 15) == 0, VRR_ERR_INVALID_ARG,
                 "qkv_rope_fwd (tcgen05): cos / sin must be 16-byte aligned");
-  QkvRopeEpi2 epi{(__nv_bfloat16*)planes, cos_tab, sin_tab, B, N, E, H, rope_mode};
+  VRR_REQUIRE(((uintptr_t)packed & 15) == 0, VRR_ERR_INVALID_ARG, "qkv_rope_fwd (tcgen05): packed table must be 16-byte aligned");
+  QkvRopeEpi2 epi{(__nv_bfloat16*)planes, cos_tab, sin_tab, reinterpret_cast<const float4*>(packed), B, N, E, H, rope_mode};
   CUtensorMap tplanes;  // planes[3 B H][N][64] bf16, box = [1][32 rows][64]
   if (int rc = make_tmap_3d_bf16(&tplanes, planes, 64, (uint64_t)N, (uint64_t)3 * B * H, 128, (uint64_t)N * 128, 64, 32)) return rc;
   // 64-column chunks are whole heads (3E = 192 H); a ragged last n-tile is clipped by the n0 < N test

@@ -75,7 +75,9 @@ int gemm_tc_variant();
 bool gemm_bf16_tc_supported(int M, int N, int K, int trans_a, int trans_b, int c_dtype, int epilogue);
 int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int trans_a,
                  int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st);
-int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const float* sin_tab, void* planes, int B, int N,
+int rope_pack_tables(const float* cos_tab, const float* sin_tab, float* packed, int heads, int rows, int hd, cudaStream_t st);
+// `packed`: optional output of rope_pack_tables for the same tables (NULL: the epilogue reads cos_tab / sin_tab)
+int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const float* sin_tab, const float* packed, void* planes, int B, int N,
                      int E, int H, int rope_mode, cudaStream_t st);
 int patch_embed_gemm_tc2(const void* unfolded, const void* weight, const void* bias, const void* pos, void* tokens, int M,
                          int Np, int K, int E, int tok_dtype, cudaStream_t st);

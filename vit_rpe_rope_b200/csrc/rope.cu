@@ -156,6 +156,30 @@ int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab,
   return VRR_OK;
 }
 
+// cos / sin tables [heads][rows][hd] -> packed[heads][hd / 2][rows] of float4 {cos[2q], sin[2q], cos[2q+1], sin[2q+1]}:
+// the layout the QKV GEMM epilogue reads.  There a LANE is a token row, so with the row-major tables one 16-byte load
+// instruction touched 32 different 128-byte lines (the table row of every lane) and the L1 tag stage, not the math,
+// set the epilogue's pace (ViT-B: 189 us with rope-mixed against 131 us without rotation); with rows innermost a
+// load instruction covers 512 contiguous bytes.
+__global__ void rope_pack_tables_kernel(const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                                        float4* __restrict__ packed, int heads, int rows, int hd) {
+  const int quads = hd >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= heads * quads * rows) return;
+  const int t = idx % rows, q = (idx / rows) % quads, h = idx / (rows * quads);
+  const size_t src = ((size_t)h * rows + t) * hd + 2 * q;
+  packed[idx] = make_float4(cos_tab[src], sin_tab[src], cos_tab[src + 1], sin_tab[src + 1]);
+}
+
+int rope_pack_tables(const float* cos_tab, const float* sin_tab, float* packed, int heads, int rows, int hd, cudaStream_t st) {
+  VRR_REQUIRE(hd % 2 == 0 && ((uintptr_t)packed & 15) == 0, VRR_ERR_INVALID_ARG,
+              "rope_pack_tables: half head dim must be even and `packed` 16-byte aligned");
+  const int total = heads * (hd / 2) * rows;
+  rope_pack_tables_kernel<<<ceil_div(total, 256), 256, 0, st>>>(cos_tab, sin_tab, reinterpret_cast<float4*>(packed), heads, rows, hd);
+  VRR_LAUNCHED();
+  return VRR_OK;
+}
+
 template <typename T>
 __global__ void rope_apply_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in,
                                   const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,

@@ -216,6 +216,20 @@ int vrr_patch_embed_bwd(const void* images, const void* d_tokens, void* d_weight
 
 int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, const float* sin_tab, void* planes,
                      int B, int N, int E, int H, int rope_mode, int dtype, void* stream) {
+  return vrr_qkv_rope_fwd_packed(x, w_qkv, cos_tab, sin_tab, nullptr, planes, B, N, E, H, rope_mode, dtype, stream);
+}
+
+int vrr_rope_pack_tables(const float* cos_tab, const float* sin_tab, float* packed, int heads, int rows, int half_dim,
+                         void* stream) {
+  VRR_REQUIRE(cos_tab && sin_tab && packed, VRR_ERR_INVALID_ARG, "rope_pack_tables: NULL pointer");
+  VRR_REQUIRE(heads > 0 && rows > 0 && half_dim > 0, VRR_ERR_INVALID_ARG, "rope_pack_tables: bad sizes");
+  if (int rc = require_device()) return rc;
+  return rope_pack_tables(cos_tab, sin_tab, packed, heads, rows, half_dim, (cudaStream_t)stream);
+}
+
+int vrr_qkv_rope_fwd_packed(const void* x, const void* w_qkv, const float* cos_tab, const float* sin_tab,
+                            const float* packed, void* planes, int B, int N, int E, int H, int rope_mode, int dtype,
+                            void* stream) {
   VRR_REQUIRE(x && w_qkv && planes, VRR_ERR_INVALID_ARG, "qkv_rope_fwd: NULL pointer");
   VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "qkv_rope_fwd: bad dtype %d", dtype);
   VRR_REQUIRE(rope_mode >= VRR_ROPE_NONE && rope_mode <= VRR_ROPE_MIXED, VRR_ERR_INVALID_ARG,
@@ -229,7 +243,7 @@ int vrr_qkv_rope_fwd(const void* x, const void* w_qkv, const float* cos_tab, con
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && qkv_rope_fwd_tc_supported(B, N, E, H)) {
     VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
     if (gemm_tc_variant() == 2)
-      return qkv_rope_fwd_tc2(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
+      return qkv_rope_fwd_tc2(x, w_qkv, cos_tab, sin_tab, packed, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
     return qkv_rope_fwd_tc(x, w_qkv, cos_tab, sin_tab, planes, B, N, E, H, rope_mode, (cudaStream_t)stream);
   }
   VRR_REQUIRE(impl != VRR_IMPL_TCGEN05, VRR_ERR_UNSUPPORTED,

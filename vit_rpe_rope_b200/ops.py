@@ -215,6 +215,28 @@ def _rope_args(cos, sin, H, N, Dh):
     return mode
 
 
+_packed_cache = {}  # device index -> (key, cos32, sin32, packed); the table tensors are held so their storage stays theirs
+
+
+def _packed_tables(cos32, sin32):
+    """``vrr_rope_pack_tables`` of the fp32 tables ([heads][half/2][rows] float4), computed once per table pair: every
+    block of a forward pass receives the SAME cos / sin storage (one shared PE module), so the repack runs once per
+    step (and once inside a captured graph).  Keyed on storage address + version counter; the cache keeps the tables
+    alive, so an address cannot be recycled for other data while its entry exists."""
+    dev = cos32.device.index
+    key = (cos32.data_ptr(), sin32.data_ptr(), cos32._version, sin32._version, tuple(cos32.shape))
+    hit = _packed_cache.get(dev)
+    if hit is not None and hit[0] == key:
+        return hit[3]
+    heads = cos32.shape[0] if cos32.ndim == 3 else 1
+    rows, half = cos32.shape[-2], cos32.shape[-1]
+    packed = torch.empty(heads, half // 2, rows, 4, device=cos32.device, dtype=torch.float32)
+    _lib.check(_lib.load().vrr_rope_pack_tables(_ptr(cos32), _ptr(sin32), _ptr(packed), heads, rows, half, _stream()),
+               "vrr_rope_pack_tables")
+    _packed_cache[dev] = (key, cos32, sin32, packed)
+    return packed
+
+
 class QkvRopeFn(torch.autograd.Function):
     """planes[3, B, H, N, Dh] = split_heads(x @ w_qkv^T), q/k rows 1.. rotated in the GEMM epilogue."""
 
@@ -232,9 +254,13 @@ class QkvRopeFn(torch.autograd.Function):
         ctx.w_grad_dtype = w_qkv.dtype
         cos32, sin32 = _f32c(cos), _f32c(sin)
         planes = torch.empty(3, B, H, N, Dh, device=x.device, dtype=x.dtype)
-        with torch.cuda.device(x.device), _timed("qkv_rope_fwd"):
-            _lib.check(lib.vrr_qkv_rope_fwd(_ptr(x), _ptr(w), _ptr(cos32), _ptr(sin32), _ptr(planes), B, N, E, H,
-                                            mode, _DT[x.dtype], _stream()), "vrr_qkv_rope_fwd")
+        with torch.cuda.device(x.device):
+            packed = None
+            if mode != _lib.ROPE_NONE and x.dtype == torch.bfloat16 and Dh == 64:  # the tcgen05 epilogue's table layout
+                packed = _packed_tables(cos32, sin32)
+            with _timed("qkv_rope_fwd"):
+                _lib.check(lib.vrr_qkv_rope_fwd_packed(_ptr(x), _ptr(w), _ptr(cos32), _ptr(sin32), _ptr(packed), _ptr(planes),
+                                                       B, N, E, H, mode, _DT[x.dtype], _stream()), "vrr_qkv_rope_fwd_packed")
         ctx.save_for_backward(x, w, planes, cos32, sin32)
         ctx.meta = (B, N, E, H, mode, None if cos is None else (cos.dtype, sin.dtype))
         return planes
