@@ -14,10 +14,10 @@ bias = torch.randn(N, device=dev)
 flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
-names = {0: "none", 1: "bias", 2: "bias+gelu (h, act)", 3: "bias+gelu (act, act')", 5: "bias+gelu (act only)"}
-for epi in (0, 1, 2, 3, 5):
+names = {0: "none", 1: "bias", 2: "bias+gelu (h, act)", 3: "bias+gelu (act, act')", 4: "multiply", 5: "bias+gelu (act only)"}
+for epi in (0, 1, 2, 3, 4, 5):
     def run():
-        rc = lib.vrr_gemm_ex(p(a), p(b), p(c), p(c2) if epi in (2, 3) else None, p(bias) if epi else None, M, N, K, 0, 1, 1, 1, epi, 0, st)
+        rc = lib.vrr_gemm_ex(p(a), p(b), p(c), p(c2) if epi in (2, 3, 4) else None, p(bias) if epi not in (0, 4) else None, M, N, K, 0, 1, 1, 1, epi, 0, st)
         assert rc == 0, _lib.last_error()
     for _ in range(3):
         run()

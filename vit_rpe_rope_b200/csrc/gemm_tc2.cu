@@ -326,21 +326,43 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         uint32_t v[64];
-        [[maybe_unused]] uint4 mv[8];  // StoreEpi::mul: this thread's 64 multipliers, in flight behind the TMEM load
+        // StoreEpi::mul: the warp's [32 rows][64] multiplier tile.  Loaded COALESCED (instruction i = rows 4i..4i+3,
+        // eight lanes x 16 bytes per row; a lane reading its own row touched 32 lines per instruction) while the TMEM
+        // load is in flight, then turned into "lane = row" through the swizzled staging buffer this chunk's output
+        // will use (its previous TMA store has been read: bulk_wait_read<1>).
+        [[maybe_unused]] uint4 mv[8];
+        [[maybe_unused]] bool with_mul = false;
         if constexpr (Epi::kTma) {
-          if (epi.mul != nullptr) {
+          with_mul = epi.mul != nullptr;
+          if (with_mul) {
             const int n0m = n_blk * BN + chalf * (BN / 2) + c * 64;
-            const int mr = m < g.M ? m : g.M - 1;
+            const int nb = max(min(n0m + (lane & 7) * 8, g.N - 8), 0);
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-              const int nb = max(min(n0m + c8 * 8, g.N - 8), 0);
-              mv[c8] = __ldg(reinterpret_cast<const uint4*>(epi.mul + (size_t)mr * g.N + nb));
+            for (int i = 0; i < 8; ++i) {
+              const int mr = min(m_warp0 + i * 4 + (lane >> 3), g.M - 1);
+              mv[i] = __ldg(reinterpret_cast<const uint4*>(epi.mul + (size_t)mr * g.N + nb));
             }
           }
         }
         __syncwarp();  // tcgen05.ld is .sync.aligned
         tmem_ld32(trow + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld32(trow + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        if constexpr (Epi::kTma) {
+          if (with_mul) {
+            const uint32_t tbuf = stage_u32 + (chunk_counter & 1u) * 4096u;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t r = (uint32_t)(i * 4 + (lane >> 3));
+              st_shared_v4(tbuf + r * 128u + ((((uint32_t)lane & 7u) ^ (r & 7u)) << 4), mv[i].x, mv[i].y, mv[i].z, mv[i].w);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8)
+              mv[c8] = ld_shared_v4(tbuf + (uint32_t)lane * 128u + ((((uint32_t)c8) ^ ((uint32_t)lane & 7u)) << 4));
+          }
+        }
         tmem_wait_ld();
         if (c == kChunks - 1) {  // this warp has read everything it needs from the accumulator stage
           tc_fence_before();
