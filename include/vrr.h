@@ -240,6 +240,15 @@ int vrr_add_layernorm_bwd(const void* dy, const void* d_xnew, const void* x_new,
                           const float* mean, const float* rstd, void* dx, void* d_branch, float* dgamma,
                           float* dbeta, int M, int E, int branch_dtype, int y_dtype, void* stream);
 
+/* fc2's input gradient with the GELU backward and fc1's bias gradient fused (autograd of timm Mlp, vit.py:118):
+ *   c[m][n] = (op(a) . op(b))[m][n] * mul[m][n]   (`dtype`, as VRR_EPI_MUL)
+ *   col_sums[n] = sum_m c[m][n]                   (fp32 [N], written; sums the values AS STORED, like autograd's
+ *                                                  sum over the bf16 tensor)
+ * bf16 on the tcgen05 kernel: the epilogue adds the column sums of each staged tile (fp32 atomics - summation
+ * order not deterministic); otherwise vrr_gemm_ex(VRR_EPI_MUL) followed by vrr_colsum. */
+int vrr_gemm_mul_colsum(const void* a, const void* b, void* c, const void* mul, float* col_sums, int M, int N,
+                        int K, int trans_a, int trans_b, int dtype, void* stream);
+
 /* Bias gradient of a Linear layer (out-proj vit.py:91, Mlp fc1/fc2 vit.py:118, head vit.py:285):
  * out[c] = sum_m x[m][c], fp32 [C] (written); x [M][C] `dtype`, C % 4 == 0. */
 int vrr_colsum(const void* x, float* out, int M, int C, int dtype, void* stream);

@@ -783,3 +783,18 @@ def test_gemm_epilogues_gelu_grad_and_mul(m, n, k):
         dx = ops._gemm(dy, w2, False, False, torch.bfloat16, epilogue=_lib.EPI_MUL, aux=mul)
     want = (dy.float() @ w2.float()) * mul.float()
     assert err_rel(dx.float(), want.cpu().numpy()) <= 1e-2
+    # the same GEMM with the column sums of its output (fc1's bias gradient) from the epilogue
+    lib = _lib.load()
+    dx2 = torch.empty_like(dx)
+    sums = torch.full((k,), float("nan"), device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    with tcgen05_must_run():
+        _lib.check(lib.vrr_gemm_mul_colsum(p(dy), p(w2), p(dx2), p(mul), p(sums), m, k, n, 0, 0, 1, st), "mul_colsum")
+    assert torch.equal(dx2, dx)
+    assert err_rel(sums, dx.float().sum(0).cpu().numpy()) <= 1e-5
+    dy32, w32_, mul32 = dy.float(), w2.float(), mul.float()  # SIMT family: same entry point, fp32
+    dx32 = torch.empty(m, k, device=DEV)
+    _lib.check(lib.vrr_gemm_mul_colsum(p(dy32), p(w32_), p(dx32), p(mul32), p(sums), m, k, n, 0, 0, 0, st), "mul_colsum f32")
+    assert err_rel(dx32, want.cpu().numpy()) <= 1e-5
+    assert err_rel(sums, dx32.sum(0).cpu().numpy()) <= 1e-5

@@ -143,6 +143,7 @@ struct StoreEpi {
                       //            2: C = bf16(gelu(h)), C2 = bf16(gelu'(h)) - what an Mlp backward needs instead of h
                       //            3: C = bf16(gelu(h)) only (inference): its own code path, one TMA store per chunk
   const __nv_bfloat16* mul;  // bf16 only, or null: C = bf16(acc * mul[m][n]) (mul is [M][N] like C): d_act * gelu'(h)
+  float* colsum;      // bf16 plain / bias / mul paths, or null: colsum[n] += sum_m C[m][n] (values as stored; atomics)
 };
 
 // gelu(h) and d gelu / dh for TWO values at a time on the packed fp32x2 pipe (fma.rn.f32x2, sm_100): the epilogue of
@@ -527,6 +528,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (store_ok) tma_store_2d(&tmap_c, my_stage + buf, n0, m_warp0);
                 bulk_commit();
               }
+              if (epi.colsum != nullptr && store_ok) {
+                // bias gradient of the layer that produced A: column sums of the tile AS STORED (bf16), read back from
+                // the staging buffer while the TMA store drains it; lane = column pair, conflict-free under the swizzle
+                // (rows past M hold zeros: their A rows were zero-filled)
+                float s0 = 0.f, s1 = 0.f;
+                const uint32_t cbase = stage_u32 + buf + ((uint32_t)lane & 3u) * 4u;
+#pragma unroll 8
+                for (uint32_t r = 0; r < 32; ++r) {
+                  const uint32_t wv = ld_shared_u32(cbase + r * 128u + ((((uint32_t)lane >> 2) ^ (r & 7u)) << 4));
+                  const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
+                  s0 += v2.x;
+                  s1 += v2.y;
+                }
+                const int col = n0 + 2 * lane;
+                if (col < g.N) {
+                  atomicAdd(epi.colsum + col, s0);
+                  atomicAdd(epi.colsum + col + 1, s1);
+                }
+              }
             }
           } else {
             // ---- fp32 C: two [32 rows][32 floats] boxes per 64-column chunk ----
@@ -640,8 +660,9 @@ int launch_pair(const void* a, const void* b, int M, int N, int K, int splits, c
 
 template <bool A_MN, bool B_MN>
 int launch_store(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int c_f32,
-                 int epilogue, int accumulate, cudaStream_t st) {
+                 int epilogue, int accumulate, float* colsum, cudaStream_t st) {
   StoreEpi epi;
+  epi.colsum = colsum;
   epi.bias = (epilogue != VRR_EPI_NONE && epilogue != VRR_EPI_MUL) ? bias : nullptr;
   epi.out_f32 = c_f32;
   epi.gelu = epilogue == VRR_EPI_BIAS_GELU ? 1 : (epilogue == VRR_EPI_BIAS_GELU_GRAD ? 2 : (epilogue == VRR_EPI_BIAS_GELU_ACT ? 3 : 0));
@@ -688,7 +709,10 @@ bool gemm_bf16_tc_supported(int M, int N, int K, int trans_a, int trans_b, int c
 }
 
 int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int trans_a,
-                 int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st) {
+                 int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st, float* colsum) {
+  VRR_REQUIRE(colsum == nullptr || (c_dtype == VRR_BF16 && epilogue != VRR_EPI_BIAS_GELU && epilogue != VRR_EPI_BIAS_GELU_GRAD &&
+                                    epilogue != VRR_EPI_BIAS_GELU_ACT),
+              VRR_ERR_UNSUPPORTED, "gemm (tcgen05): column sums come with the bf16 plain / bias / multiply epilogues only");
   VRR_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)c2) & 15) == 0, VRR_ERR_INVALID_ARG,
               "gemm (tcgen05): a / b / c must be 16-byte aligned");
   VRR_REQUIRE(epilogue == VRR_EPI_NONE || epilogue == VRR_EPI_MUL || (bias != nullptr && ((uintptr_t)bias & 15) == 0),
@@ -698,10 +722,10 @@ int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* b
   VRR_REQUIRE(!accumulate || c_dtype == VRR_F32, VRR_ERR_UNSUPPORTED, "gemm (tcgen05): accumulate needs an fp32 C");
   const int c_f32 = c_dtype == VRR_F32;
   const bool a_mn = trans_a != 0, b_mn = trans_b == 0;
-  if (!a_mn && !b_mn) return launch_store<false, false>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, st);
-  if (!a_mn && b_mn) return launch_store<false, true>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, st);
-  if (a_mn && b_mn) return launch_store<true, true>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, st);
-  return launch_store<true, false>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, st);
+  if (!a_mn && !b_mn) return launch_store<false, false>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, colsum, st);
+  if (!a_mn && b_mn) return launch_store<false, true>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, colsum, st);
+  if (a_mn && b_mn) return launch_store<true, true>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, colsum, st);
+  return launch_store<true, false>(a, b, c, c2, bias, M, N, K, c_f32, epilogue, accumulate, colsum, st);
 }
 
 // ---- QKV projection + RoPE epilogue on the CTA-pair kernel -----------------------------------------------

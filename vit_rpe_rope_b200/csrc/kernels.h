@@ -74,7 +74,8 @@ void gemm_tc_set_variant(int v);  // 2 (default): CTA-pair kernels; 1: the 1-CTA
 int gemm_tc_variant();
 bool gemm_bf16_tc_supported(int M, int N, int K, int trans_a, int trans_b, int c_dtype, int epilogue);
 int gemm_bf16_tc(const void* a, const void* b, void* c, void* c2, const float* bias, int M, int N, int K, int trans_a,
-                 int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st);
+                 int trans_b, int c_dtype, int epilogue, int accumulate, cudaStream_t st, float* colsum = nullptr);
+// colsum (bf16 C, plain / bias / multiply epilogues): colsum[n] += sum_m C[m][n] of the values as stored; zeroed by the caller
 int rope_pack_tables(const float* cos_tab, const float* sin_tab, float* packed, int heads, int rows, int hd, cudaStream_t st);
 // `packed`: optional output of rope_pack_tables for the same tables (NULL: the epilogue reads cos_tab / sin_tab)
 int qkv_rope_fwd_tc2(const void* x, const void* w, const float* cos_tab, const float* sin_tab, const float* packed, void* planes, int B, int N,

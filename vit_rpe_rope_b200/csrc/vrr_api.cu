@@ -342,6 +342,24 @@ int vrr_gemm_ex(const void* a, const void* b, void* c, void* c2, const float* bi
   return gemm_simt(a, b, c, M, N, K, trans_a, trans_b, dtype, c_dtype, (cudaStream_t)stream);
 }
 
+int vrr_gemm_mul_colsum(const void* a, const void* b, void* c, const void* mul, float* col_sums, int M, int N, int K,
+                        int trans_a, int trans_b, int dtype, void* stream) {
+  VRR_REQUIRE(a && b && c && mul && col_sums, VRR_ERR_INVALID_ARG, "gemm_mul_colsum: NULL pointer");
+  VRR_REQUIRE(M > 0 && N > 0 && K > 0 && N % 4 == 0, VRR_ERR_INVALID_ARG, "gemm_mul_colsum: bad sizes (N %% 4 == 0)");
+  VRR_REQUIRE(dtype_ok(dtype), VRR_ERR_INVALID_ARG, "gemm_mul_colsum: bad dtype %d", dtype);
+  if (int rc = require_device()) return rc;
+  const int impl = g_impl.load();
+  if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && gemm_bf16_tc_supported(M, N, K, trans_a, trans_b, VRR_BF16, VRR_EPI_MUL)) {
+    VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
+    VRR_CUDA(cudaMemsetAsync(col_sums, 0, (size_t)N * sizeof(float), (cudaStream_t)stream));
+    return gemm_bf16_tc(a, b, c, const_cast<void*>(mul), nullptr, M, N, K, trans_a, trans_b, VRR_BF16, VRR_EPI_MUL, 0,
+                        (cudaStream_t)stream, col_sums);
+  }
+  if (int rc = vrr_gemm_ex(a, b, c, const_cast<void*>(mul), nullptr, M, N, K, trans_a, trans_b, dtype, dtype, VRR_EPI_MUL, 0, stream))
+    return rc;
+  return colsum(c, col_sums, M, N, dtype, (cudaStream_t)stream);
+}
+
 int vrr_attn_fwd(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B, int H, int N,
                  int Dh, float scale, int dtype, void* stream) {
   VRR_REQUIRE(planes && out && lse, VRR_ERR_INVALID_ARG, "attn_fwd: NULL pointer");

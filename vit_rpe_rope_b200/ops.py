@@ -11,6 +11,7 @@ PyTorch is used for device memory, streams and autograd plumbing only; all arith
 paths runs in the hand-written sm_100a kernels.  CUDA only - CPU tensors raise.
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -547,6 +548,9 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+_FUSE_DB1 = os.environ.get("VRR_FUSE_DB1", "1") != "0"  # A/B switch: fc1's bias gradient inside fc2's dX GEMM
+
+
 class MlpFn(torch.autograd.Function):
     """fc1 -> exact GELU -> fc2 (timm Mlp, models/vit.py:118).  fc1's GEMM epilogue adds the bias and writes BOTH
     gelu(h) and gelu'(h) (h itself is never stored: the backward only needs the derivative); fc2 adds its bias.
@@ -578,11 +582,24 @@ class MlpFn(torch.autograd.Function):
         if dy2.dtype != x2.dtype:
             dy2 = dy2.to(x2.dtype)
         with torch.cuda.device(dy.device):
-            dh = _gemm(dy2, w2l, False, False, x2.dtype, epilogue=_lib.EPI_MUL, aux=gp, name="fc2_dx")
+            # dh = (dy . W2) * gelu'(h) with fc1's bias gradient (column sums of dh as stored, like autograd's sum
+            # over the rounded tensor) accumulated by the same GEMM's epilogue
+            if _FUSE_DB1:
+                lib = _lib.load()
+                M, N, K = dy2.shape[0], w2l.shape[1], dy2.shape[1]
+                dh = torch.empty(M, N, device=dy2.device, dtype=x2.dtype)
+                db1 = torch.empty(N, device=dy2.device, dtype=torch.float32)
+                with _timed("fc2_dx"):
+                    _lib.check(lib.vrr_gemm_mul_colsum(_ptr(dy2), _ptr(w2l), _ptr(dh), _ptr(gp), _ptr(db1), M, N, K, 0, 0,
+                                                       _DT[x2.dtype], _stream()), "vrr_gemm_mul_colsum")
+                db1 = db1.to(b1_dt)
+            else:
+                dh = _gemm(dy2, w2l, False, False, x2.dtype, epilogue=_lib.EPI_MUL, aux=gp, name="fc2_dx")
+                with _timed("colsum"):
+                    db1 = _colsum(dh).to(b1_dt)
             dw2 = _gemm(dy2, a2, True, False, w2_dt, name="fc2_dw")
             with _timed("colsum"):
                 db2 = _colsum(dy2).to(b2_dt)
-                db1 = _colsum(dh).to(b1_dt)  # sums the values as stored (rounded), like autograd's sum over dh
             dx = _gemm(dh, w1l, False, False, x2.dtype, name="fc1_dx").view(x_shape)
             dw1 = _gemm(dh, x2, True, False, w1_dt, name="fc1_dw")
         return dx, dw1, db1, dw2, db2, None, None
