@@ -35,7 +35,10 @@
 //     serialise); 32-byte TMA boxes need 4 KB per warp, which two resident items do not leave;
 //   * a second register buffer to keep the next chunk's tcgen05.ld in flight: slower (2 620 -> 3 400 cycles per 128
 //     columns).  The exponentials run at ~50-60 % of the MUFU roof (16 ex2 / clk / SM, scripts/ubench/mufu.cu) -
-//     P is evaluated twice per element (once per orientation), which is the price of keeping dS out of shared memory.
+//     P is evaluated twice per element (once per orientation), which is the price of keeping dS out of shared memory;
+//   * process16 on the packed fp32x2 pipe (fma / add / mul .f32x2): 349 us (132 registers instead of 113), and on top of
+//     it a share of the exponentials by the FMA-pipe polynomial tc::ex2_poly2: +5 us per pair of eight (350 -> 371 us
+//     at 6 of 8) - the column groups are bound by instruction issue and register traffic, not by MUFU throughput.
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"

@@ -415,25 +415,6 @@ __device__ __forceinline__ float v4_max16m(const uint32_t (&r)[16], float mx, in
     return mx;
   }
 }
-// 2^x for two values WITHOUT the MUFU unit: x = n + f with n = round(x) (magic-number add), f in [-0.5, 0.5];
-// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5 - P is rounded to bf16, 3.9e-3, right after) and n
-// added into the exponent field.  ~5 FMA-pipe instructions per value on the packed fp32x2 pipe: MUFU.EX2 issues 16
-// per clock per SM against 32 softmax elements per clock the tensor pipe could consume at head dim 64, so a share
-// of the exponentials computed here raises the kernel's MUFU-bound ceiling.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x = make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f));
-  const float2 magic = make_float2(12582912.f, 12582912.f);  // 1.5 * 2^23: the integer lands in the low mantissa bits
-  const float2 t = __fadd2_rn(x, magic);
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
-  float2 q = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), f, make_float2(0.2426111251f, 0.2426111251f));
-  q = __ffma2_rn(q, f, make_float2(0.6932609677f, 0.6932609677f));
-  q = __ffma2_rn(q, f, make_float2(0.9999280572f, 0.9999280572f));
-  // (bits(t) << 23) == (n << 23) modulo 2^32: the magic constant's low nine bits are zero
-  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
-}
-
 // P = 2^(s * scale - m) for 16 scores -> 8 packed bf16x2; the row sum accumulates in l2.  POLY of the 8 pairs take
 // the polynomial, the others MUFU.EX2.
 template <bool FULL, int POLY>
