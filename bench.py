@@ -259,7 +259,7 @@ def main():
     import torch.distributed as dist
     from vit_rpe_rope_b200 import VisionTransformer, _lib, ops
     from vit_rpe_rope_b200.dp import BucketedDataParallel
-    from vit_rpe_rope_b200.runtime import GraphedTrainStep
+    from vit_rpe_rope_b200.runtime import GraphedInference, GraphedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,7 +292,6 @@ def main():
     torch.manual_seed(0)
     model = VisionTransformer(**mcfg).to(dev)
     train = wl["train"]
-    use_graph = use_graph and train
     dp = BucketedDataParallel(model, bucket_mb=32.0) if train else None
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=use_graph) \
         if train else None
@@ -310,12 +309,23 @@ def main():
                                   use_graph=use_graph, warmup=max(3, args.warmup))
         runner.prepare(dev_images, dev_labels)
 
+    inf_runner = None
+    if not train:
+        inf_runner = GraphedInference(model, tuple(host_images.shape), dev, bf16=bf16, use_graph=use_graph,
+                                      warmup=max(3, args.warmup))
+
     def infer(images):
+        return inf_runner.run(images)
+
+    def infer_eager(images):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
             return model(images)
 
+    if inf_runner is not None:
+        inf_runner.static_images.copy_(dev_images)  # `value`: the batch is already where the captured forward reads it
+
     def step_resident():
-        return runner.run() if train else infer(dev_images)
+        return runner.run() if train else inf_runner.run()
 
     def barrier():
         if world > 1:
@@ -345,7 +355,10 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    gpu_launches = (runner.launches_per_step * args.steps) if (train and use_graph) else _lib.launch_count() - launches0
+    if use_graph:
+        gpu_launches = (runner.launches_per_step if train else inf_runner.launches_per_step) * args.steps
+    else:
+        gpu_launches = _lib.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- per-launch kernel timing (CUDA events on the launching stream) -> `roofline`.  A graph replay has
@@ -353,7 +366,7 @@ def main():
     # every libvrr launch; the kernels and their inputs are identical to the timed region's.
     ops.PROFILE_EVENTS = []
     for _ in range(args.steps):
-        runner._eager_step() if train else infer(dev_images)
+        runner._eager_step() if train else infer_eager(dev_images)
     torch.cuda.synchronize()
     events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
     kernel_ms = {}
@@ -420,6 +433,8 @@ def main():
         multi-rank runs had printed their result and then stalled inside destroy_process_group()."""
         if runner is not None:
             runner.close()
+        if inf_runner is not None:
+            inf_runner.close()
         if world > 1:
             import signal
             sys.stdout.flush()

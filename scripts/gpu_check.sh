@@ -26,6 +26,12 @@ for w in $what; do
         timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
         echo "bench $wl exit: $?"; tail -2 gpurun_out/bench_$wl.err; cat gpurun_out/bench_$wl.json
       done ;;
+    sweep5)  # BASELINE configs[4]: batch sweep of the 1025-token inference config (per GPU; the 8-GPU run is 8 replicas)
+      for bs in 1 8 32 64 128; do
+        timeout 300 python bench.py --workload vitb16-512-rope-mixed-infer-bf16 --batch $bs --steps 20 --warmup 5 --no-cpu-baseline --no-reference-gpu \
+          > gpurun_out/bench_cfg5_b$bs.json 2> gpurun_out/bench_cfg5_b$bs.err
+        echo "cfg5 batch $bs exit: $?"; cut -c1-160 gpurun_out/bench_cfg5_b$bs.json
+      done ;;
     kbench)
       for geo in vitb vitl x512; do timeout 300 python scripts/kbench.py $geo > gpurun_out/kbench_$geo.log 2>&1; cat gpurun_out/kbench_$geo.log; done ;;
     launches)

@@ -300,6 +300,26 @@ def test_cfg5_resolution_extrapolation_inference_bf16():
     _bf16_model_case(kw, batch=2, size=512, train=False)
 
 
+def test_graphed_inference_replays_the_eager_forward():
+    """runtime.GraphedInference: the captured forward returns what the eager forward returns, for fresh inputs
+    (the RoPE tables and their packed copy are rebuilt inside the graph), and counts its launches."""
+    from vit_rpe_rope_b200.models.vit import VisionTransformer
+    from vit_rpe_rope_b200.runtime import GraphedInference
+    torch.manual_seed(0)
+    model = VisionTransformer(img_size=64, patch_size=8, in_chans=3, num_classes=10, embed_dim=256, depth=2, num_heads=4,
+                              pos_encoding="rope-mixed").to(DEV).eval()
+    runner = GraphedInference(model, (4, 3, 96, 96), torch.device(DEV), bf16=True)  # 145 tokens: resolution extrapolation
+    assert runner.graph is not None and runner.launches_per_step > 0
+    g = torch.Generator().manual_seed(7)
+    for _ in range(3):
+        x = torch.randn(4, 3, 96, 96, generator=g).to(DEV)
+        got = runner.run(x).float().clone()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want = model(x).float()
+        assert torch.equal(got, want)
+    runner.close()
+
+
 # ------------------------------------------------------------------------------------- kernels vs numpy
 
 def _planes(b, h, n, d, dtype, seed=0):

@@ -148,3 +148,49 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = None
         torch.cuda.synchronize()
+
+
+class GraphedInference:
+    """``model(images)`` under ``no_grad`` (and bf16 autocast) captured once and replayed with one launch: at small
+    batches the ~90 launches of a ViT-B forward cost more than the kernels (batch 1 at 1025 tokens: 4.5 ms eager).
+    ``run(images)`` copies the batch into the graph's static input and returns the static output tensor."""
+
+    def __init__(self, model, images_shape, device, bf16: bool = True, use_graph: bool = True, warmup: int = 3):
+        self.model, self.bf16, self.device = model, bf16, device
+        self.static_images = torch.zeros(images_shape, device=device, dtype=torch.float32)
+        self.static_out = None
+        self.graph = None
+        self.launches_per_step = 0
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                before = _lib.launch_count()
+                self.static_out = self._eager()
+                self.launches_per_step = _lib.launch_count() - before
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_out = self._eager()
+            torch.cuda.synchronize()
+
+    def _eager(self):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
+            return self.model(self.static_images)
+
+    def run(self, images=None):
+        if images is not None and images is not self.static_images:
+            self.static_images.copy_(images, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.static_out = self._eager()
+        return self.static_out
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.graph = None
+        torch.cuda.synchronize()
+
