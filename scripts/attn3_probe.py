@@ -130,6 +130,6 @@ if "time" in what:
             t = timeit(lambda: torch.autograd.grad(o, [pl], d_out, retain_graph=True))
             line += f" | bwd {t * 1e3:8.1f} us {2 * fl / t / 1e9:7.1f} TF {2 * by / t / 1e6:7.1f} GB/s"
             print(line, flush=True)
-    setopt("attn_fwd_variant", 3)
+    setopt("attn_fwd_variant", 4)
     setopt("attn_bwd_variant", 3)
 sys.exit(0 if all_ok else 1)

@@ -92,7 +92,8 @@ def timeit(b, h, n, kind="none", reps=10):
 
 ok = True
 if "check" in what:
-    for (b, h, n) in [(1, 2, 257), (2, 3, 300), (1, 2, 577), (2, 2, 1025), (1, 1, 64 * 5 + 1), (1, 2, 130)]:
+    for (b, h, n) in [(1, 2, 257), (2, 3, 300), (1, 2, 577), (2, 2, 1025), (1, 1, 64 * 5 + 1), (1, 2, 130), (2, 2, 336), (1, 3, 368),
+                      (2, 2, 384)]:
         for kind in ("none", "table", "poly", "poly_heads"):
             ok &= check(b, h, n, kind)
     print("PARITY", "OK" if ok else "FAILED")
@@ -102,6 +103,10 @@ if "time" in what:
     timeit(32, 12, 1025)
     timeit(16, 12, 577, "table")
     timeit(16, 12, 577, "poly")
+    timeit(256, 12, 197)  # N <= 256: the whole-sequence kernel serves every column above ...
+    setopt("attn_fwd_variant", 2)  # ... unless the long-sequence kernels are forced: 2-CTA / 4-CTA at short sequences
     timeit(256, 12, 197)
+    timeit(512, 4, 65)
+    setopt("attn_fwd_variant", 4)
 setopt("attn_fwd_streams", 4)
 sys.exit(0 if ok else 1)

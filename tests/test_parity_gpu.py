@@ -671,10 +671,14 @@ def test_persistent_attention_many_items_per_cta(b, h, n):
     g = torch.Generator().manual_seed(22)
     d_out = (torch.randn(b, n, h * d, generator=g) * 0.5).to(torch.bfloat16)
     scale = d ** -0.5
-    with tcgen05_must_run():
-        out = ops.fused_attention(planes, scale)
-        out.backward(d_out.to(DEV))
-    out2 = ops.fused_attention(planes.detach(), scale)
+    _set_option("attn_fwd_variant", 3)  # the whole-sequence forward (the default without bias is the four-CTA kernel)
+    try:
+        with tcgen05_must_run():
+            out = ops.fused_attention(planes, scale)
+            out.backward(d_out.to(DEV))
+        out2 = ops.fused_attention(planes.detach(), scale)
+    finally:
+        _set_option("attn_fwd_variant", 4)
     assert torch.equal(out, out2), "persistent forward is not reproducible run to run"
     pl = planes.detach().double().cpu().numpy()
     o_np, _, _, _ = A.attention_forward(pl[0], pl[1], pl[2], scale, None)
@@ -699,18 +703,20 @@ def test_attention_kernel_variants_agree(n):
     d_out = (torch.randn(b, n, h * d, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
     res = {}
     try:
-        for variant in (3, 2):
+        for variant in (4, 3, 2):
             _set_option("attn_fwd_variant", variant)
-            _set_option("attn_bwd_variant", variant)
+            _set_option("attn_bwd_variant", min(variant, 3))
             pl = planes.clone().requires_grad_(True)
             out = ops.fused_attention(pl, d ** -0.5)
             out.backward(d_out)
             res[variant] = (out.detach().float(), pl.grad.float())
     finally:
-        _set_option("attn_fwd_variant", 3)
+        _set_option("attn_fwd_variant", 4)
         _set_option("attn_bwd_variant", 3)
     assert err_rel(res[3][0], res[2][0].cpu().numpy()) <= 1e-2
+    assert err_rel(res[4][0], res[2][0].cpu().numpy()) <= 1e-2
     assert err_rel(res[3][1], res[2][1].cpu().numpy()) <= BF16_TOL
+    assert err_rel(res[4][1], res[2][1].cpu().numpy()) <= BF16_TOL
 
 
 @pytest.mark.parametrize("rope", ["axial", "mixed"])

@@ -443,15 +443,27 @@ __device__ __forceinline__ void v4_tile(uint32_t trow, int nvalid, int t, float 
   uint32_t(&a)[16] = *reinterpret_cast<uint32_t(*)[16]>(&ab[0]);
   uint32_t(&b)[16] = *reinterpret_cast<uint32_t(*)[16]>(&ab[16]);
   // ---- pass 1: tile max (two 32-column loads: one TMEM round trip less than four 16-column ones) ----
+  // The ragged LAST tile (every ViT sequence is 64 k + a few tokens: 65, 197, 577, 1025) was issued as a narrow MMA of
+  // nc = round16(nvalid) columns and is walked in nc / 16 chunks only.
   float tmax = -INFINITY;
-  tmem_ld32(trow, ab);
-  tmem_wait_ld();
-  tmax = v4_max16m<FULL>(a, tmax, 0, nvalid);
-  tmax = v4_max16m<FULL>(b, tmax, 16, nvalid);
-  tmem_ld32(trow + 32, ab);
-  tmem_wait_ld();
-  tmax = v4_max16m<FULL>(a, tmax, 32, nvalid);
-  tmax = v4_max16m<FULL>(b, tmax, 48, nvalid) * scale_log2;
+  const int nchunks = FULL ? 4 : (nvalid + 15) >> 4;
+  if (FULL) {
+    tmem_ld32(trow, ab);
+    tmem_wait_ld();
+    tmax = v4_max16(a, tmax);
+    tmax = v4_max16(b, tmax);
+    tmem_ld32(trow + 32, ab);
+    tmem_wait_ld();
+    tmax = v4_max16(a, tmax);
+    tmax = v4_max16(b, tmax);
+  } else {
+    for (int c = 0; c < nchunks; ++c) {
+      tmem_ld16(trow + c * 16, a);
+      tmem_wait_ld();
+      tmax = v4_max16m<false>(a, tmax, c * 16, nvalid);
+    }
+  }
+  tmax *= scale_log2;
   tmem_ld16(trow, a);  // first chunk of pass 2
   const bool jump = tmax > m_ref + thr;
   if (__any_sync(0xffffffffu, jump)) {
@@ -476,21 +488,30 @@ __device__ __forceinline__ void v4_tile(uint32_t trow, int nvalid, int t, float 
   const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_ref, -m_ref);
   float2 l2 = make_float2(0.f, 0.f);
   uint32_t pk[8];
-  tmem_wait_ld();
-  tmem_ld16(trow + 16, b);
-  v4_exp16<FULL, POLY>(a, pk, sc2, nm2, l2, 0, nvalid);
-  tmem_st8(trow, pk);  // columns [0,8): scores already consumed
-  tmem_wait_ld();
-  tmem_ld16(trow + 32, a);
-  v4_exp16<FULL, POLY>(b, pk, sc2, nm2, l2, 16, nvalid);
-  tmem_st8(trow + 8, pk);
-  tmem_wait_ld();
-  tmem_ld16(trow + 48, b);
-  v4_exp16<FULL, POLY>(a, pk, sc2, nm2, l2, 32, nvalid);
-  tmem_st8(trow + 16, pk);
-  tmem_wait_ld();
-  v4_exp16<FULL, POLY>(b, pk, sc2, nm2, l2, 48, nvalid);
-  tmem_st8(trow + 24, pk);
+  if (FULL) {
+    tmem_wait_ld();
+    tmem_ld16(trow + 16, b);
+    v4_exp16<true, POLY>(a, pk, sc2, nm2, l2, 0, nvalid);
+    tmem_st8(trow, pk);  // columns [0,8): scores already consumed
+    tmem_wait_ld();
+    tmem_ld16(trow + 32, a);
+    v4_exp16<true, POLY>(b, pk, sc2, nm2, l2, 16, nvalid);
+    tmem_st8(trow + 8, pk);
+    tmem_wait_ld();
+    tmem_ld16(trow + 48, b);
+    v4_exp16<true, POLY>(a, pk, sc2, nm2, l2, 32, nvalid);
+    tmem_st8(trow + 16, pk);
+    tmem_wait_ld();
+    v4_exp16<true, POLY>(b, pk, sc2, nm2, l2, 48, nvalid);
+    tmem_st8(trow + 24, pk);
+  } else {
+    for (int c = 0; c < nchunks; ++c) {
+      if (c > 0) tmem_ld16(trow + c * 16, a);
+      tmem_wait_ld();
+      v4_exp16<false, POLY>(a, pk, sc2, nm2, l2, c * 16, nvalid);
+      tmem_st8(trow + c * 8, pk);  // columns [8c, 8c+8) lie below every chunk still to be read
+    }
+  }
   l_run += l2.x + l2.y;
   tmem_wait_st();
 }
@@ -568,10 +589,14 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p)
     mbar_wait(bar_q, 0);
     mbar_wait(&bar_kfull[0], 0);
     tc_fence_after();
+    // the ragged last tile is a narrow MMA: N = round16(valid keys) instead of 64
+    const int last_cols = (N - (ntiles - 1) * kKT + 15) & ~15;
+    const uint32_t idesc_s_last = idesc_bf16(kM, last_cols, 0, 0);
     if (elect_one()) {
       const uint64_t desc_k = smem_desc_sw128(smem_u32(sK));
+      const uint32_t id0 = ntiles == 1 ? idesc_s_last : idesc_s;
 #pragma unroll
-      for (int k = 0; k < kDh / 16; ++k) mma_ss(tmem_base, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k > 0);
+      for (int k = 0; k < kDh / 16; ++k) mma_ss(tmem_base, desc_q + 2 * k, desc_k + 2 * k, id0, k > 0);
       mma_commit(bar_s);
       mma_commit(&bar_kempty[0]);
     }
@@ -611,8 +636,9 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p)
         mma_commit(&bar_vempty[stage]);
         if (t + 1 < ntiles) {
           const uint64_t desc_k = smem_desc_sw128(smem_u32(sK + ((t + 1) & 1) * kTileBytes));
+          const uint32_t idn = (t + 2 == ntiles) ? idesc_s_last : idesc_s;
 #pragma unroll
-          for (int k = 0; k < kDh / 16; ++k) mma_ss(tmem_base, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k > 0);
+          for (int k = 0; k < kDh / 16; ++k) mma_ss(tmem_base, desc_q + 2 * k, desc_k + 2 * k, idn, k > 0);
           mma_commit(bar_s);
           mma_commit(&bar_kempty[(t + 1) & 1]);
         } else {

@@ -25,7 +25,9 @@ constexpr int kMaxDevices = 64;
 static std::atomic<int> g_dev_state[kMaxDevices];
 static std::atomic<int> g_dev_sms[kMaxDevices];
 std::atomic<uint64_t> g_family_launches[3];  // [VRR_IMPL_SIMT], [VRR_IMPL_TCGEN05] dispatch counters
-static std::atomic<int> g_attn_fwd_variant{3};  // 3: whole-sequence kernel for N <= 256 (attn_fwd_ws.cu), else attn_tc.cu; 2: attn_tc.cu always
+// 4: without bias the four-CTA kernel of attn_tc.cu at every N, with bias as 3;  3: whole-sequence kernel for N <= 256
+// (attn_fwd_ws.cu), else attn_tc.cu;  2: attn_tc.cu always
+static std::atomic<int> g_attn_fwd_variant{4};
 static std::atomic<int> g_attn_bwd_variant{3};  // 3: attn_bwd_ws.cu for N <= 208 without bias, else attn_bwd_tc2.cu; 2: attn_bwd_tc2.cu always
 
 int current_device() {
@@ -372,7 +374,8 @@ int vrr_attn_fwd(const void* planes, const vrr_bias_desc* bias, void* out, float
   if (dtype == VRR_BF16 && impl != VRR_IMPL_SIMT && attn_fwd_tc_supported(B, H, N, Dh, bias)) {
     VRR_COUNT_FAMILY(VRR_IMPL_TCGEN05);
     const int variant = g_attn_fwd_variant.load();
-    if (variant >= 3 && attn_fwd_ws_supported(B, H, N, Dh, bias))  // short sequences: whole-sequence kernel
+    const bool no_bias = bias == nullptr || bias->mode == VRR_BIAS_NONE;
+    if (variant >= 3 && !(variant >= 4 && no_bias) && attn_fwd_ws_supported(B, H, N, Dh, bias))  // short sequences with bias
       return attn_fwd_ws(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
     return attn_fwd_tc(planes, bias, out, lse, B, H, N, Dh, scale, (cudaStream_t)stream);
   }
