@@ -317,6 +317,8 @@ def test_graphed_inference_replays_the_eager_forward():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             want = model(x).float()
         assert torch.equal(got, want)
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+            assert torch.equal(model(x).float(), want)  # inference tensors (no version counters) take the same path
     runner.close()
 
 
@@ -756,6 +758,12 @@ def test_qkv_rope_packed_tables_bit_identical(rope, b, n, e, h):
     out2 = ops.QkvRopeFn.apply(x, w, cs, sn, h)
     _lib.check(lib.vrr_qkv_rope_fwd(p(x), p(w), p(cos), p(sin), p(plain), b, n, e, h, mode, 1, st), "plain")
     assert torch.equal(out2, plain) and not torch.equal(out1, out2)
+    with torch.inference_mode():  # inference tensors have no version counter: the cache must step aside, not raise
+        ang2 = torch.rand(heads, n - 1, dh // 2, device=DEV) * 6.0
+        c2, s2 = torch.cos(ang2), torch.sin(ang2)
+        out3 = ops.QkvRopeFn.apply(x, w, c2 if rope == "mixed" else c2[0], s2 if rope == "mixed" else s2[0], h)
+    _lib.check(lib.vrr_qkv_rope_fwd(p(x), p(w), p(c2), p(s2), p(plain), b, n, e, h, mode, 1, st), "plain")
+    assert torch.equal(out3, plain)
 
 
 @pytest.mark.parametrize("b,h,n", [(2, 3, 257), (1, 2, 577), (3, 2, 641), (1, 2, 1025)])

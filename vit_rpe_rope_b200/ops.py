@@ -225,16 +225,20 @@ def _packed_tables(cos32, sin32):
     step (and once inside a captured graph).  Keyed on storage address + version counter; the cache keeps the tables
     alive, so an address cannot be recycled for other data while its entry exists."""
     dev = cos32.device.index
-    key = (cos32.data_ptr(), sin32.data_ptr(), cos32._version, sin32._version, tuple(cos32.shape))
+    try:
+        key = (cos32.data_ptr(), sin32.data_ptr(), cos32._version, sin32._version, tuple(cos32.shape))
+    except RuntimeError:  # tensors made under torch.inference_mode() carry no version counter: repack every call
+        key = None
     hit = _packed_cache.get(dev)
-    if hit is not None and hit[0] == key:
+    if key is not None and hit is not None and hit[0] == key:
         return hit[3]
     heads = cos32.shape[0] if cos32.ndim == 3 else 1
     rows, half = cos32.shape[-2], cos32.shape[-1]
     packed = torch.empty(heads, half // 2, rows, 4, device=cos32.device, dtype=torch.float32)
     _lib.check(_lib.load().vrr_rope_pack_tables(_ptr(cos32), _ptr(sin32), _ptr(packed), heads, rows, half, _stream()),
                "vrr_rope_pack_tables")
-    _packed_cache[dev] = (key, cos32, sin32, packed)
+    if key is not None:
+        _packed_cache[dev] = (key, cos32, sin32, packed)
     return packed
 
 
