@@ -184,5 +184,7 @@ class RoPEMixed(nn.Module):
             phase_y = t_y.view(1, -1, 1) * self.freqs[1].unsqueeze(-2)
             phase_x = phase_x.view(seq_len, self.num_heads, -1).permute(1, 0, 2)
             phase_y = phase_y.view(seq_len, self.num_heads, -1).permute(1, 0, 2)
-            phase = phase_x + phase_y
+            # (contiguous: the sum of two permuted views keeps their strides, and every block would re-copy the
+            # two tables before handing them to the kernels)
+            phase = (phase_x + phase_y).contiguous()
             return torch.cos(phase), torch.sin(phase)

@@ -148,6 +148,8 @@ class PatchEmbedFn(torch.autograd.Function):
                                                _DT[tdt], _stream()), "vrr_patch_embed_fwd")
         if ctx.needs_input_grad[0]:
             ctx.w_for_dimg = w
+        # the tcgen05 path's workspace IS unfold(images) [B*Np][C*P*P] bf16: the weight-gradient GEMM reuses it
+        ctx.unfolded = ws if (ws is not None and ws_bytes == B * Np * C * patch * patch * 2) else None
         ctx.save_for_backward(images)
         ctx.meta = (B, C, Hi, Wi, patch, E, Np, pos_embed.shape if pos_embed is not None else None,
                     weight.shape, cls_token.shape, idt, dt, tdt)
@@ -173,10 +175,14 @@ class PatchEmbedFn(torch.autograd.Function):
                                                _ptr(d_pos_rows), B, C, Hi, Wi, patch, E, _DT[idt], _DT[dt], _DT[tdt],
                                                _stream()), "vrr_patch_embed_bwd")
             if not own_dw:
-                unf = torch.empty(B * Np, K, device=dev, dtype=torch.bfloat16)
-                _lib.check(lib.vrr_patch_unfold(_ptr(images), _ptr(unf), B, C, Hi, Wi, patch, _DT[idt], _stream()),
-                           "vrr_patch_unfold")
-                g = d_tokens[:, 1:, :].reshape(B * Np, E).to(torch.bfloat16)
+                if ctx.unfolded is not None:
+                    unf = ctx.unfolded.view(torch.bfloat16).view(B * Np, K)
+                else:
+                    unf = torch.empty(B * Np, K, device=dev, dtype=torch.bfloat16)
+                    _lib.check(lib.vrr_patch_unfold(_ptr(images), _ptr(unf), B, C, Hi, Wi, patch, _DT[idt], _stream()),
+                               "vrr_patch_unfold")
+                # cast first: one strided read + packed bf16 write (reshaping the fp32 slice first copied 154 MB twice)
+                g = d_tokens[:, 1:, :].to(torch.bfloat16).reshape(B * Np, E)
                 d_w = _gemm(g, unf, True, False, torch.float32, name="patch_dw")
         d_pos = None
         if pos_shape is not None:
