@@ -171,6 +171,12 @@ class VisionTransformer(nn.Module):
 
     def forward_features(self, x):
         """[B, C, H, W] -> [B, N, E] with N = (H/P)(W/P) + 1 taken from the input (vit.py:235-271)."""
+        x, m = self._features(x)
+        return x if m is None else x + m
+
+    def _features(self, x):
+        """The token stream before the LAST residual add and that add's branch (or the finished stream and None):
+        ``forward`` only needs the cls row of the sum."""
         B, C, H, W = x.shape
         h, w = H // self.patch_size, W // self.patch_size
         if x.is_cuda:  # one multi-tensor refresh of the bf16 weight copies per forward (no-op in fp32)
@@ -186,20 +192,19 @@ class VisionTransformer(nn.Module):
         if not self._fusable(x):
             for blk in self.blocks:
                 x = blk(x, freqs_cis=freqs_cis)
-            return x
+            return x, None
         # Same arithmetic as the loop above (vit.py:120-125 per block), with every residual add fused with
         # the LayerNorm that follows it - also across block boundaries:
         #   x = x + attn(norm1(x));  x = x + mlp(norm2(x))
         blocks = self.blocks
         y = ops.layer_norm(x, blocks[0].norm1)
+        m = None
         for i, blk in enumerate(blocks):
             x, y = ops.add_layer_norm(x, blk.attn(y, freqs_cis=freqs_cis), blk.norm2)
             m = blk.mlp(y)
             if i + 1 < len(blocks):
                 x, y = ops.add_layer_norm(x, m, blocks[i + 1].norm1)
-            else:
-                x = x + m
-        return x
+        return x, m
 
     def _gemm_weights(self):
         ws = [self.head.weight]
@@ -216,8 +221,9 @@ class VisionTransformer(nn.Module):
             for blk in self.blocks)
 
     def forward(self, x):
-        x = self.forward_features(x)
-        # LayerNorm is per token and only the cls token reaches the head (vit.py:284-285): normalising
-        # that row alone gives identical logits and gradients
-        y = ops.layer_norm(x[:, 0], self.norm)
+        x, m = self._features(x)
+        # LayerNorm is per token and only the cls token reaches the head (vit.py:284-285): the last residual
+        # add and the final norm of that row alone give identical logits and gradients
+        cls = x[:, 0] if m is None else x[:, 0] + m[:, 0]
+        y = ops.layer_norm(cls, self.norm)
         return ops.linear(y, self.head, ops.lp_weight(self.head.weight, ops.compute_dtype(y)))
