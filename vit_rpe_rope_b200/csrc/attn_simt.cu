@@ -82,6 +82,42 @@ struct AttnShape {
   float scale;
   int bias_mode, bias_heads, bias_len, bias_grid;
   const float* bias_param;
+  int poly_pw;  // dQ kernel, polynomial bias of degree <= 3: per-thread power sums instead of the shared histogram
+};
+
+// Positional bias of (own token, streamed token).  Relative table: index i - j + N - 1; polynomial: LUT over the L1
+// grid distance.  The own token's grid coordinates are computed once per thread and the streamed tile's once per
+// tile (32 entries of shared memory): the first version divided twice per ELEMENT, which made the polynomial mode
+// 1.4x (forward) to 1.7x (backward) slower than the table mode at ViT-Tiny.
+struct RowBias {
+  int mode, n;
+  const float* lut;
+  const int* tyx;  // POLY: (y << 8 | x) of the streamed tile's tokens
+  int self, ys, xs;
+  bool self_is_query;
+  __device__ __forceinline__ void init(int mode_, int n_, int grid, const float* lut_, const int* tyx_, int self_, bool q) {
+    mode = mode_; n = n_; lut = lut_; tyx = tyx_; self = self_; self_is_query = q;
+    const int ps = self_ > 0 ? self_ - 1 : 0;
+    ys = grid > 0 ? ps % grid : 0;
+    xs = grid > 0 ? ps / grid : 0;
+  }
+  // call by every thread right after the tile loads, before the __syncthreads that publishes the tile
+  __device__ __forceinline__ void fill_tile(int* tyx_w, int j0, int grid) const {
+    if (mode == VRR_BIAS_POLY && threadIdx.x < kTile) {
+      const int t = j0 + (int)threadIdx.x, pt = t > 0 ? t - 1 : 0;
+      tyx_w[threadIdx.x] = ((pt % grid) << 8) | (pt / grid);
+    }
+  }
+  __device__ __forceinline__ int index(int other, int jl) const {
+    if (mode == VRR_BIAS_TABLE) return (self_is_query ? self - other : other - self) + n - 1;
+    const int yx = tyx[jl];
+    return abs(ys - (yx >> 8)) + abs(xs - (yx & 255));
+  }
+  __device__ __forceinline__ float at(int other, int jl) const {
+    if (mode == VRR_BIAS_NONE) return 0.f;
+    if (mode == VRR_BIAS_POLY && (self == 0 || other == 0)) return 0.f;
+    return lut[index(other, jl)];
+  }
 };
 
 // ------------------------------------------------------------------------------------------ forward
@@ -92,7 +128,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_simt_kernel(const T* __rest
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;
   float* Vs = Ks + kTile * DH;
-  float* lut = Vs + kTile * DH;
+  int* tyx = reinterpret_cast<int*>(Vs + kTile * DH);
+  float* lut = reinterpret_cast<float*>(tyx + kTile);
 
   const int bh = blockIdx.y, b = bh / sh.H, h = bh % sh.H, N = sh.N;
   const int half = threadIdx.x & 1;
@@ -104,7 +141,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_simt_kernel(const T* __rest
   const T* vg = kg + plane;
 
   fill_bias_lut(lut, sh.bias_mode, sh.bias_param, sh.bias_heads, sh.bias_len, sh.bias_grid, N, h);
-  BiasView bias{sh.bias_mode, N, sh.bias_grid, lut};
+  RowBias bias;
+  bias.init(sh.bias_mode, N, sh.bias_grid, lut, tyx, ic, true);
 
   float q[DH / 2], acc[DH / 2];
   load_half_row<T, DH>(qg + (size_t)ic * DH, half, q);
@@ -117,13 +155,14 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_simt_kernel(const T* __rest
     __syncthreads();
     load_tile<T, DH>(Ks, kg + (size_t)j0 * DH, rows);
     load_tile<T, DH>(Vs, vg + (size_t)j0 * DH, rows);
+    bias.fill_tile(tyx, j0, sh.bias_grid);
     __syncthreads();
     float s[kTile];
     float tmax = -INFINITY;
 #pragma unroll
     for (int j = 0; j < kTile; ++j) {
       float d = pair_sum(half_dot<DH>(q, Ks + j * DH, half));
-      float v = (j < rows) ? d * sh.scale + bias.at(ic, j0 + j) : -INFINITY;
+      float v = (j < rows) ? d * sh.scale + bias.at(j0 + j, j) : -INFINITY;
       s[j] = v;
       tmax = fmaxf(tmax, v);
     }
@@ -158,7 +197,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_simt_kernel(
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;
   float* Vs = Ks + kTile * DH;
-  float* lut = Vs + kTile * DH;
+  int* tyx = reinterpret_cast<int*>(Vs + kTile * DH);
+  float* lut = reinterpret_cast<float*>(tyx + kTile);
   const int lut_len = (sh.bias_mode == VRR_BIAS_TABLE) ? 2 * sh.N - 1
                       : (sh.bias_mode == VRR_BIAS_POLY ? 2 * sh.bias_grid - 1 : 0);
   float* hist = lut + lut_len;
@@ -175,7 +215,9 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_simt_kernel(
 
   fill_bias_lut(lut, sh.bias_mode, sh.bias_param, sh.bias_heads, sh.bias_len, sh.bias_grid, N, h);
   for (int t = threadIdx.x; t < lut_len; t += kThreads) hist[t] = 0.f;
-  BiasView bias{sh.bias_mode, N, sh.bias_grid, lut};
+  RowBias bias;
+  bias.init(sh.bias_mode, N, sh.bias_grid, lut, tyx, ic, true);
+  float pw0 = 0.f, pw1 = 0.f, pw2 = 0.f, pw3 = 0.f;  // poly_pw: sum of dS * distance^k over this thread's elements
 
   float q[DH / 2], go[DH / 2], dq[DH / 2];
   load_half_row<T, DH>(qg + (size_t)ic * DH, half, q);
@@ -199,6 +241,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_simt_kernel(
     __syncthreads();
     load_tile<T, DH>(Ks, kg + (size_t)j0 * DH, rows);
     load_tile<T, DH>(Vs, vg + (size_t)j0 * DH, rows);
+    bias.fill_tile(tyx, j0, sh.bias_grid);
     __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < kTile; ++j) {
@@ -206,15 +249,41 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_simt_kernel(
       float dp = pair_sum(half_dot<DH>(go, Vs + j * DH, half));
       const int jj = j0 + j;
       const bool ok = live && j < rows;
-      float p = ok ? expf(s * sh.scale + bias.at(ic, jj) - li) : 0.f;
+      float p = ok ? expf(s * sh.scale + bias.at(jj, j) - li) : 0.f;
       float ds = p * (dp - dl);
       half_axpy<DH>(dq, ds, Ks + j * DH, half);
       if (ok && half == 0 && sh.bias_mode != VRR_BIAS_NONE &&
-          !(sh.bias_mode == VRR_BIAS_POLY && (ic == 0 || jj == 0)))
-        atomicAdd(&hist[bias.index(ic, jj)], ds);
+          !(sh.bias_mode == VRR_BIAS_POLY && (ic == 0 || jj == 0))) {
+        if (sh.poly_pw) {  // d_coef[k] = sum dS * distance^k: no atomics in the loop (15 bins, every thread of the CTA)
+          const float dist = (float)bias.index(jj, j);
+          pw0 += ds;
+          const float w1 = ds * dist;
+          pw1 += w1;
+          const float w2 = w1 * dist;
+          pw2 += w2;
+          pw3 = fmaf(w2, dist, pw3);
+        } else {
+          atomicAdd(&hist[bias.index(jj, j)], ds);
+        }
+      }
     }
   }
   if (live) store_half_row<T, DH>(d_planes + ((size_t)bh * N + i) * DH, half, dq, sh.scale);
+  if (sh.poly_pw) {  // warp sums -> hist[0..3] (which the tail below adds to d_lut[h][0..3])
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pw0 += __shfl_xor_sync(0xffffffffu, pw0, o);
+      pw1 += __shfl_xor_sync(0xffffffffu, pw1, o);
+      pw2 += __shfl_xor_sync(0xffffffffu, pw2, o);
+      pw3 += __shfl_xor_sync(0xffffffffu, pw3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&hist[0], pw0);
+      atomicAdd(&hist[1], pw1);
+      atomicAdd(&hist[2], pw2);
+      atomicAdd(&hist[3], pw3);
+    }
+  }
   if (lut_len) {
     __syncthreads();
     float* dst = d_lut + (size_t)h * lut_len;
@@ -236,7 +305,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_simt_kernel(
   float* Gs = Qs + kTile * DH;   // dO tile
   float* Ls = Gs + kTile * DH;   // lse tile
   float* Ds = Ls + kTile;        // delta tile
-  float* lut = Ds + kTile;
+  int* tyx = reinterpret_cast<int*>(Ds + kTile);
+  float* lut = reinterpret_cast<float*>(tyx + kTile);
 
   const int bh = blockIdx.y, b = bh / sh.H, h = bh % sh.H, N = sh.N, E = sh.H * DH;
   const int half = threadIdx.x & 1;
@@ -249,7 +319,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_simt_kernel(
   const T* vg = kg + plane;
 
   fill_bias_lut(lut, sh.bias_mode, sh.bias_param, sh.bias_heads, sh.bias_len, sh.bias_grid, N, h);
-  BiasView bias{sh.bias_mode, N, sh.bias_grid, lut};
+  RowBias bias;
+  bias.init(sh.bias_mode, N, sh.bias_grid, lut, tyx, jc, false);
 
   float k[DH / 2], v[DH / 2], dk[DH / 2], dv[DH / 2];
   load_half_row<T, DH>(kg + (size_t)jc * DH, half, k);
@@ -273,13 +344,14 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_simt_kernel(
       Ls[r] = (r < rows) ? lse[(size_t)bh * N + i0 + r] : 0.f;
       Ds[r] = (r < rows) ? delta[(size_t)bh * N + i0 + r] : 0.f;
     }
+    bias.fill_tile(tyx, i0, sh.bias_grid);
     __syncthreads();
 #pragma unroll 4
     for (int r = 0; r < kTile; ++r) {
       float s = pair_sum(half_dot<DH>(k, Qs + r * DH, half));
       float dp = pair_sum(half_dot<DH>(v, Gs + r * DH, half));
       const bool ok = live && r < rows;
-      float p = ok ? expf(s * sh.scale + bias.at(i0 + r, jc) - Ls[r]) : 0.f;
+      float p = ok ? expf(s * sh.scale + bias.at(i0 + r, r) - Ls[r]) : 0.f;
       float ds = p * (dp - Ds[r]);
       half_axpy<DH>(dv, p, Gs + r * DH, half);
       half_axpy<DH>(dk, ds, Qs + r * DH, half);
@@ -292,13 +364,18 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_simt_kernel(
 }
 
 // d_coef[hc][k] = sum over heads (if shared) and distances of d_lut[h][d] * d^k
+// (pw_mode: d_lut[h][k] already holds sum dS * distance^k - only the heads are summed)
 __global__ void poly_coef_grad_kernel(const float* __restrict__ d_lut, float* __restrict__ d_coef,
-                                      int H, int coef_heads, int len, int lut_len) {
+                                      int H, int coef_heads, int len, int lut_len, int pw_mode) {
   int hc = blockIdx.x, k = threadIdx.x;
   if (k >= len) return;
   double acc = 0.0;
   for (int h = 0; h < H; ++h) {
     if (coef_heads != 1 && h != hc) continue;
+    if (pw_mode) {
+      acc += (double)d_lut[(size_t)h * lut_len + k];
+      continue;
+    }
     for (int d = 0; d < lut_len; ++d) {
       double pw = 1.0;
       for (int e = 0; e < k; ++e) pw *= (double)d;
@@ -310,7 +387,7 @@ __global__ void poly_coef_grad_kernel(const float* __restrict__ d_lut, float* __
 
 // ------------------------------------------------------------------------------------------ host
 static AttnShape make_shape(int B, int H, int N, float scale, const vrr_bias_desc* bias) {
-  AttnShape sh{B, H, N, scale, VRR_BIAS_NONE, 0, 0, 0, nullptr};
+  AttnShape sh{B, H, N, scale, VRR_BIAS_NONE, 0, 0, 0, nullptr, 0};
   if (bias && bias->mode != VRR_BIAS_NONE) {
     sh.bias_mode = bias->mode; sh.bias_heads = bias->heads; sh.bias_len = bias->len;
     sh.bias_grid = bias->grid; sh.bias_param = bias->param;
@@ -322,7 +399,7 @@ template <typename T, int DH>
 static int fwd_launch(const void* planes, const vrr_bias_desc* bias, void* out, float* lse, int B,
                       int H, int N, float scale, cudaStream_t st) {
   AttnShape sh = make_shape(B, H, N, scale, bias);
-  size_t smem = (size_t)(2 * kTile * DH + bias_lut_len(bias, N)) * sizeof(float);
+  size_t smem = (size_t)(2 * kTile * DH + kTile + bias_lut_len(bias, N)) * sizeof(float);
   auto kern = attn_fwd_simt_kernel<T, DH>;
   if (smem > 48 * 1024) VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(N, kRows), B * H);
@@ -344,9 +421,11 @@ static int bwd_launch(const void* planes, const vrr_bias_desc* bias, const void*
     d_lut = (sh.bias_mode == VRR_BIAS_TABLE) ? d_bias_param : d_lut_ws;
     VRR_CUDA(cudaMemsetAsync(d_lut, 0, (size_t)H * lut_len * sizeof(float), st));
   }
+  // polynomial of degree <= 3 (the reference's default): per-thread power sums; the histogram needs >= 4 bins to carry them
+  sh.poly_pw = (sh.bias_mode == VRR_BIAS_POLY && sh.bias_len <= 4 && lut_len >= 4) ? 1 : 0;
   dim3 grid(ceil_div(N, kRows), B * H);
   {
-    size_t smem = (size_t)(2 * kTile * DH + 2 * lut_len) * sizeof(float);
+    size_t smem = (size_t)(2 * kTile * DH + kTile + 2 * lut_len) * sizeof(float);
     auto kern = attn_bwd_dq_simt_kernel<T, DH>;
     if (smem > 48 * 1024) VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>((const T*)planes, (const T*)out, (const T*)d_out, lse,
@@ -354,14 +433,14 @@ static int bwd_launch(const void* planes, const vrr_bias_desc* bias, const void*
     VRR_LAUNCHED();
   }
   {
-    size_t smem = (size_t)(2 * kTile * DH + 2 * kTile + lut_len) * sizeof(float);
+    size_t smem = (size_t)(2 * kTile * DH + 3 * kTile + lut_len) * sizeof(float);
     auto kern = attn_bwd_dkv_simt_kernel<T, DH>;
     if (smem > 48 * 1024) VRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>((const T*)planes, (const T*)d_out, lse, delta, (T*)d_planes, sh);
     VRR_LAUNCHED();
   }
   if (sh.bias_mode == VRR_BIAS_POLY) {
-    poly_coef_grad_kernel<<<bias->heads, 32, 0, st>>>(d_lut, d_bias_param, H, bias->heads, bias->len, lut_len);
+    poly_coef_grad_kernel<<<bias->heads, 32, 0, st>>>(d_lut, d_bias_param, H, bias->heads, bias->len, lut_len, sh.poly_pw);
     VRR_LAUNCHED();
   }
   return VRR_OK;
