@@ -202,8 +202,12 @@ int ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float
 template <typename TX, typename TY>
 int ln_bwd_t(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
              float* dgamma, float* dbeta, int M, int E, cudaStream_t st) {
-  VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
-  VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+  if (dbeta == dgamma + E) {  // the two rows of one [2][E] buffer (what ops.py allocates): one memset node instead of two
+    VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)2 * E * sizeof(float), st));
+  } else {
+    VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
+    VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+  }
   if (E % 128 == 0) return ln_bwd_launch<TX, TY, 4>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
   return ln_bwd_launch<TX, TY, 1>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, E, st);
 }
@@ -543,8 +547,12 @@ template <typename TB, typename TY>
 int add_ln_bwd_t(const void* dy, const float* d_xnew, const float* x_new, const float* gamma, const float* mean,
                  const float* rstd, float* dx, void* d_branch, float* dgamma, float* dbeta, int M, int E,
                  cudaStream_t st) {
-  VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
-  VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+  if (dbeta == dgamma + E) {  // the two rows of one [2][E] buffer (what ops.py allocates): one memset node instead of two
+    VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)2 * E * sizeof(float), st));
+  } else {
+    VRR_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)E * sizeof(float), st));
+    VRR_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)E * sizeof(float), st));
+  }
 #define VRR_LN_BWD_GO(NV, W, B)                                                                                          \
   auto kern = add_ln_bwd_reg_kernel<TB, TY, NV, W, B>;                                                                 \
   VRR_SMEM_ATTR_ONCE(kern, 160 * 1024);                                                                                \

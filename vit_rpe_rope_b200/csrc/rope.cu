@@ -132,8 +132,12 @@ int qkv_rope_bwd(const void* d_planes, const void* planes, const float* cos_tab,
   if (rope_mode == VRR_ROPE_NONE) d_cos = d_sin = nullptr;
   if (d_cos) {
     size_t n = (size_t)(rope_mode == VRR_ROPE_MIXED ? H : 1) * (N - 1) * hd * sizeof(float);
-    VRR_CUDA(cudaMemsetAsync(d_cos, 0, n, st));
-    VRR_CUDA(cudaMemsetAsync(d_sin, 0, n, st));
+    if (reinterpret_cast<char*>(d_sin) == reinterpret_cast<char*>(d_cos) + n) {  // halves of one buffer: one memset node
+      VRR_CUDA(cudaMemsetAsync(d_cos, 0, 2 * n, st));
+    } else {
+      VRR_CUDA(cudaMemsetAsync(d_cos, 0, n, st));
+      VRR_CUDA(cudaMemsetAsync(d_sin, 0, n, st));
+    }
   }
   const int vec = dtype == VRR_F32 ? 4 : 8;
   VRR_REQUIRE(hd % vec == 0, VRR_ERR_UNSUPPORTED, "qkv_rope_bwd: head dim %d too small for %d-wide access", Dh, vec);

@@ -284,8 +284,10 @@ class QkvRopeFn(torch.autograd.Function):
         d_planes = d_planes.contiguous()
         dev, dt = x.device, x.dtype
         need_cs = mode != _lib.ROPE_NONE and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
-        d_cos = torch.empty_like(cos32) if need_cs else None
-        d_sin = torch.empty_like(sin32) if need_cs else None
+        d_cos = d_sin = None
+        if need_cs:  # halves of one buffer: zeroed by one memset
+            d_cs = torch.empty((2,) + tuple(cos32.shape), device=dev, dtype=torch.float32)
+            d_cos, d_sin = d_cs[0], d_cs[1]
         d_qkv = torch.empty(B * N, 3 * E, device=dev, dtype=dt)
         with torch.cuda.device(dev):
             _lib.check(lib.vrr_qkv_rope_bwd(_ptr(d_planes), _ptr(planes), _ptr(cos32), _ptr(sin32), _ptr(d_qkv),
@@ -423,8 +425,8 @@ class LayerNormFn(torch.autograd.Function):
         if dy2.dtype != out_dtype:
             dy2 = dy2.to(out_dtype)
         dx = torch.empty_like(x2)
-        dg = torch.empty(E, device=x2.device, dtype=torch.float32)
-        db = torch.empty(E, device=x2.device, dtype=torch.float32)
+        dgb = torch.empty(2, E, device=x2.device, dtype=torch.float32)  # one buffer: zeroed by one memset
+        dg, db = dgb[0], dgb[1]
         with torch.cuda.device(x2.device), _timed("layernorm_bwd"):
             _lib.check(lib.vrr_layernorm_bwd(_ptr(dy2), _ptr(x2), _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dg),
                                              _ptr(db), M, E, _DT[x2.dtype], _DT[out_dtype], _stream()),
@@ -476,8 +478,8 @@ class AddLayerNormFn(torch.autograd.Function):
                 dr2 = dr2.float()
         dx = torch.empty_like(x_new)
         d_branch = torch.empty(M, E, device=x_new.device, dtype=br_dtype)
-        dg = torch.empty(E, device=x_new.device, dtype=torch.float32)
-        db = torch.empty(E, device=x_new.device, dtype=torch.float32)
+        dgb = torch.empty(2, E, device=x_new.device, dtype=torch.float32)  # one buffer: the library zeroes both rows with one memset
+        dg, db = dgb[0], dgb[1]
         with torch.cuda.device(x_new.device), _timed("add_layernorm_bwd"):
             _lib.check(lib.vrr_add_layernorm_bwd(_ptr(dy2), _ptr(dr2), _ptr(x_new), _ptr(w32), _ptr(mean), _ptr(rstd),
                                                  _ptr(dx), _ptr(d_branch), _ptr(dg), _ptr(db), M, E, _DT[br_dtype],
