@@ -31,6 +31,38 @@ def test_header_symbols_exported(lib):
     assert set(_lib.SIGNATURES) == set(names)
 
 
+def _prototypes():
+    """name -> list of parameter kinds ('p' pointer, 'i' int, 'f' float, 'z' size_t) parsed from the header."""
+    src = open(_lib.HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(vrr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        params = [q.strip() for q in m.group(2).split(",") if q.strip() and q.strip() != "void"]
+        kinds = []
+        for q in params:
+            if "*" in q:
+                kinds.append("p")
+            elif re.match(r"(const\s+)?float\b", q):
+                kinds.append("f")
+            elif re.match(r"(const\s+)?size_t\b", q):
+                kinds.append("z")
+            else:
+                kinds.append("i")
+        out[m.group(1)] = kinds
+    return out
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every ctypes argtypes list has the header prototype's parameter count and pointer / int / float kinds: a
+    drifted binding would pass garbage through the C ABI without any error."""
+    kind_of = {ctypes.c_void_p: "p", ctypes.c_char_p: "p", ctypes.c_int: "i", ctypes.c_float: "f", ctypes.c_size_t: "z"}
+    protos = _prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        got = ["p" if (isinstance(a, type) and issubclass(a, ctypes._Pointer)) else kind_of[a] for a in argtypes]
+        assert got == protos[name], (name, got, protos[name])
+
+
 def test_abi_version_and_enums(lib):
     assert lib.vrr_abi_version() == 1
     hdr = open(_lib.HEADER_PATH).read()
