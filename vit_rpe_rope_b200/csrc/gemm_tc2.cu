@@ -450,39 +450,48 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 bulk_commit();
               }
             } else if (epi.gelu != 0) {
-              // two outputs: (h, gelu(h)) or (gelu(h), gelu'(h)).  The chunk is computed into registers FIRST and only
-              // then waits for the previous chunk's TMA stores to release the two staging buffers.
-              uint32_t o0[32], o1[32];
+              // two outputs: (h, gelu(h)) or (gelu(h), gelu'(h)).  Computed and flushed to the staging buffers in two
+              // halves of 32 columns: the profile of the one-piece version was 58 % fixed-latency dependency stalls
+              // (`stall_wait`) - with 64 packed outputs held next to the 64 accumulators ptxas had no registers left
+              // to interleave the per-pair chains.  The first half is computed BEFORE the wait for the previous
+              // chunk's TMA stores.
 #pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) {
-                const int nb = min(n0 + c8 * 8, g.N - 8);  // N % 8 == 0; clamp keeps the tail read in bounds
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb + 4));
-                const uint32_t br[4] = {pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w)};
+              for (int hf = 0; hf < 2; ++hf) {
+                uint32_t o0[16], o1[16];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&br[j]));  // bias as bf16
-                  const float2 hs = __fadd2_rn(make_float2(f[c8 * 8 + 2 * j], f[c8 * 8 + 2 * j + 1]), bb);
-                  const uint32_t hw = pack_bf16(hs.x, hs.y);
-                  const float2 hr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));  // h as stored
-                  float2 gl, dg;
-                  gelu_and_grad2(hr, gl, dg);
-                  if (epi.gelu == 1) {
-                    o0[c8 * 4 + j] = hw;
-                    o1[c8 * 4 + j] = pack_bf16(gl.x, gl.y);
-                  } else {
-                    o0[c8 * 4 + j] = pack_bf16(gl.x, gl.y);
-                    o1[c8 * 4 + j] = pack_bf16(dg.x, dg.y);
+                for (int q = 0; q < 4; ++q) {
+                  const int c8 = hf * 4 + q;
+                  const int nb = min(n0 + c8 * 8, g.N - 8);  // N % 8 == 0; clamp keeps the tail read in bounds
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + nb + 4));
+                  const uint32_t br[4] = {pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w)};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&br[j]));  // bias as bf16
+                    const float2 hs = __fadd2_rn(make_float2(f[c8 * 8 + 2 * j], f[c8 * 8 + 2 * j + 1]), bb);
+                    const uint32_t hw = pack_bf16(hs.x, hs.y);
+                    const float2 hr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));  // h as stored
+                    float2 gl, dg;
+                    gelu_and_grad2(hr, gl, dg);
+                    if (epi.gelu == 1) {
+                      o0[q * 4 + j] = hw;
+                      o1[q * 4 + j] = pack_bf16(gl.x, gl.y);
+                    } else {
+                      o0[q * 4 + j] = pack_bf16(gl.x, gl.y);
+                      o1[q * 4 + j] = pack_bf16(dg.x, dg.y);
+                    }
                   }
                 }
-              }
-              if (lane == 0) bulk_wait_read<0>();
-              __syncwarp();
+                if (hf == 0) {
+                  if (lane == 0) bulk_wait_read<0>();
+                  __syncwarp();
+                }
 #pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) {
-                const uint32_t off = (((uint32_t)c8 ^ sw) << 4);
-                st_shared_v4(row_base + off, o0[c8 * 4], o0[c8 * 4 + 1], o0[c8 * 4 + 2], o0[c8 * 4 + 3]);
-                st_shared_v4(row_base + 4096u + off, o1[c8 * 4], o1[c8 * 4 + 1], o1[c8 * 4 + 2], o1[c8 * 4 + 3]);
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t off = (((uint32_t)(hf * 4 + q) ^ sw) << 4);
+                  st_shared_v4(row_base + off, o0[q * 4], o0[q * 4 + 1], o0[q * 4 + 2], o0[q * 4 + 3]);
+                  st_shared_v4(row_base + 4096u + off, o1[q * 4], o1[q * 4 + 1], o1[q * 4 + 2], o1[q * 4 + 3]);
+                }
               }
               fence_proxy_async_smem();
               __syncwarp();
