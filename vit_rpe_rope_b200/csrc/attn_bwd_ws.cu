@@ -38,7 +38,8 @@
 //     P is evaluated twice per element (once per orientation), which is the price of keeping dS out of shared memory;
 //   * process16 on the packed fp32x2 pipe (fma / add / mul .f32x2): 349 us (132 registers instead of 113), and on top of
 //     it a share of the exponentials by the FMA-pipe polynomial tc::ex2_poly2: +5 us per pair of eight (350 -> 371 us
-//     at 6 of 8) - the column groups are bound by instruction issue and register traffic, not by MUFU throughput.
+//     at 6 of 8) - the column groups are bound by instruction issue and register traffic, not by MUFU throughput;
+//   * two 16-column chunks per loop iteration (four tcgen05.ld in flight, 168 registers, no spills): 308 us - no gain.
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
